@@ -1,0 +1,171 @@
+"""Pin the CPU oracle to outputs of the reference itself (tests/golden/*.npz, made by
+tests/golden/make_golden.py in the build container).  CPU only."""
+import numpy as np
+import torch
+
+from conftest import load_golden
+from oracle import adjacency, knn, losses, propagation, ranking
+
+RTOL = 1e-5
+
+
+def close(a, b, rtol=RTOL, atol=1e-7):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    assert a.shape == b.shape
+    assert np.abs(a - b).max() <= rtol * scale + atol, (np.abs(a - b).max(), scale)
+
+
+def coo_equal(t, idx, val):
+    t = t.coalesce()
+    order = np.lexsort((idx[1], idx[0]))
+    assert np.array_equal(t.indices().numpy(), idx[:, order])
+    assert np.array_equal(t.values().numpy(), val[order])  # bit-exact fp32
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def test_adjacency_bit_exact(mini_ds):
+    g = load_golden("clussl_mini.npz")
+    ds = mini_ds
+    coo_equal(adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items),
+              g["adj/norm_adj_matrix/idx"], g["adj/norm_adj_matrix/val"])
+    coo_equal(adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients),
+              g["adj/ingre_norm_adj/idx"], g["adj/ingre_norm_adj/val"])
+    coo_equal(adjacency.norm_adj_item_side(ds.image_cluster_triples, ds.n_items, ds.cfg.n_cluster),
+              g["adj/image_norm_adj/idx"], g["adj/image_norm_adj/val"])
+    coo_equal(adjacency.norm_adj_item_side(ds.text_cluster_triples, ds.n_items, ds.cfg.n_cluster),
+              g["adj/text_norm_adj/idx"], g["adj/text_norm_adj/val"])
+
+
+def _clussl(ds, g, grad=False):
+    S_ui = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    S_g = adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients)
+    S_v = adjacency.norm_adj_item_side(ds.image_cluster_triples, ds.n_items, ds.cfg.n_cluster)
+    S_t = adjacency.norm_adj_item_side(ds.text_cluster_triples, ds.n_items, ds.cfg.n_cluster)
+    P = {k: T(g["sd/" + k]).clone().requires_grad_(grad) for k in (
+        "user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight",
+        "image_prototype_embedding.weight", "text_prototype_embedding.weight")}
+    out = propagation.clussl_forward(
+        S_ui, S_g, S_v, S_t, P["user_embedding.weight"], P["item_embedding.weight"],
+        P["ingre_embedding.weight"], P["image_prototype_embedding.weight"],
+        P["text_prototype_embedding.weight"], ds.n_users, ds.n_items, ds.num_ingredients,
+        ds.cfg.n_cluster, 2, 1)
+    return P, out
+
+
+def test_clussl_forward_loss_grad(mini_ds):
+    g = load_golden("clussl_mini.npz")
+    P, (ua, ia, (vi, vt, vg)) = _clussl(mini_ds, g)
+    for got, key in ((ua, "user_all"), (ia, "item_all"), (vi, "item_image"), (vt, "item_text"), (vg, "item_ingre")):
+        close(got.numpy(), g["fwd/" + key])
+    for b in range(2):
+        P, out = _clussl(mini_ds, g, grad=True)
+        u, p, n = (T(g[f"batch/{b}/{k}"]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+        terms = losses.clussl_loss(out, P["user_embedding.weight"], P["item_embedding.weight"], u, p, n, 0.01, 0.1)
+        close([float(t) for t in terms], g[f"loss/{b}"])
+        sum(terms).sum().backward()
+        for k, v in P.items():
+            # padding_idx row of ingre_embedding receives no gradient in nn.Embedding
+            # distance-correlation backward cancels heavily in fp32: two orderings of the same
+            # ops differ by ~1e-4 of the gradient's max, so grads are held to 5e-4 (losses to 1e-5)
+            got = v.grad.numpy().copy()
+            close(got, g[f"grad/{k}/{b}"], rtol=5e-4)
+    close(ranking.inference_scores(ua, ia, torch.full((len(g["infer/cand"]),), 3), T(g["infer/cand"])).numpy(),
+          g["infer/scores"])
+
+
+def test_healthrec_forward(mini_ds, mini_batches):
+    g = load_golden("healthrec_mini.npz")
+    ds = mini_ds
+    S_ui = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    S_ri = adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients)
+    coo_equal(S_ri, g["adj/ri_norm_adj/idx"], g["adj/ri_norm_adj/val"])
+    uw, iw, gw = (T(g["sd/" + k]) for k in ("user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight"))
+    ua, ia, ing = propagation.healthrec_forward(S_ui, S_ri, uw, iw, gw, ds.n_users, ds.n_items,
+                                               ds.num_ingredients, 2, 1)
+    close(ua.numpy(), g["fwd/user_all"])
+    close(ia.numpy(), g["fwd/item_all"])
+    close(ing.numpy(), g["fwd/ingre_ir"])
+    for b, batch in enumerate(mini_batches):
+        u, p, n = (T(batch[k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+        mf = losses.bpr_from_tables(ua, ia, u, p, n)
+        reg = 0.5 * losses.emb_loss(uw[u], iw[p], iw[n], gw[T(batch["pos_ingre_code"])],
+                                    gw[T(batch["neg_ingre_code"])])
+        close([float(mf), float(reg)], g[f"loss/{b}"][[0, 3]])
+
+
+def test_lightgcn_forward(mini_ds, mini_batches):
+    g = load_golden("lightgcn_mini.npz")
+    ds = mini_ds
+    S_ui = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    ego = T(g["sd/image_embedding.weight"]) @ T(g["sd/image_trs.weight"]).t() + T(g["sd/image_trs.bias"])
+    ua, ia = propagation.lightgcn_forward(S_ui, T(g["sd/user_embedding.weight"]), ego, ds.n_users, ds.n_items, 2)
+    close(ua.numpy(), g["fwd/user_all"])
+    close(ia.numpy(), g["fwd/item_all"])
+    for b, batch in enumerate(mini_batches):
+        u, p, n = (T(batch[k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+        close(float(losses.bpr_from_tables(ua, ia, u, p, n)), g[f"loss/{b}"][0])
+
+
+def test_loss_primitives():
+    g = load_golden("primitives.npz")
+    close(losses.bpr_loss(T(g["bpr/pos"]), T(g["bpr/neg"])).numpy(), g["bpr/out"])
+    close(losses.emb_loss(T(g["emb/e1"]), T(g["emb/e2"]), T(g["emb/e3"])).numpy(), g["emb/out"])
+    x, y = T(g["dcor/x"]).requires_grad_(True), T(g["dcor/y"]).requires_grad_(True)
+    d = losses.correlation_distance(x, y)
+    d.backward()
+    close(d.detach().numpy(), g["dcor/out"])
+    close(x.grad.numpy(), g["dcor/gx"], rtol=1e-4)
+    close(y.grad.numpy(), g["dcor/gy"], rtol=1e-4)
+    h = T(g["nce/h"]).requires_grad_(True)
+    c = losses.info_nce(h)
+    c.backward()
+    close(c.detach().numpy(), g["nce/out"])
+    close(h.grad.numpy(), g["nce/gh"], rtol=1e-4)
+
+
+def test_knn_utilities(mini_ds):
+    g = load_golden("primitives.npz")
+    sim = knn.build_sim(T(g["knn/feat"]))
+    close(sim.numpy(), g["knn/sim"])
+    nb, val, ind = knn.knn_neighbourhood(T(g["knn/sim"]), 7)
+    assert np.array_equal(ind.numpy(), g["knn/topk_ind"])
+    close(nb.numpy(), g["knn/nb"])
+    close(knn.normalized_laplacian(nb).numpy(), g["knn/lap"])
+    close(knn.normalized_laplacian(nb).numpy(), g["knn/dense_sym"])
+    got = knn.centroid_topk(mini_ds.embImage[:64], mini_ds.image_center, 6)
+    assert np.array_equal(got, g["centroid/top6"])
+    from foodrec_b200.synth import topk_nearest_centres
+    assert np.array_equal(topk_nearest_centres(mini_ds.embImage[:64], mini_ds.image_center, 6), g["centroid/top6"])
+
+
+def test_ranking_and_metrics():
+    g = load_golden("primitives.npz")
+    ue, ie = T(g["rank/ue"]), T(g["rank/ie"])
+    _, topi = ranking.full_sort_topk(ue, ie, torch.arange(ue.shape[0]), 50)
+    assert np.array_equal(topi.numpy(), g["rank/topi"])
+    ptr, idx = g["rank/pos_ptr"], g["rank/pos_idx"]
+    pos = [idx[ptr[u]:ptr[u + 1]].tolist() for u in range(len(ptr) - 1)]
+    res = ranking.topk_metrics(g["rank/topi"], pos)
+    for k, v in zip(g["rank/metric_keys"], g["rank/metric_vals"]):
+        assert res[str(k)] == v, (k, res[str(k)], v)
+    toy = ranking.topk_metrics(np.array([[4, 1, 7], [0, 2, 9], [5, 6, 3], [8, 8, 1]]),
+                               [[1], [9, 0], [2], [1, 8, 4]], topk=(1, 3))
+    for k, v in zip(g["rank/toy_keys"], g["rank/toy_vals"]):
+        assert toy[str(k)] == v, (k, toy[str(k)], v)
+    r, n = ranking.metrics_by_user([3, 0, 9, 1, 7], [0, 1])
+    a = ranking.auc_fast(2, np.array([0.9, 0.1, 0.5, 0.3, 0.05, 0.7]), 4)
+    close([r, n, a], g["rank/by_user"])
+
+
+def test_history_mask_oracle():
+    torch.manual_seed(0)
+    ue, ie = torch.randn(5, 8), torch.randn(30, 8)
+    ptr = np.array([0, 3, 3, 10, 12, 15])
+    idx = np.random.default_rng(0).integers(0, 30, size=15)
+    _, top = ranking.full_sort_topk(ue, ie, torch.arange(5), 6, ptr, idx)
+    for u in range(5):
+        assert not set(top[u].tolist()) & set(idx[ptr[u]:ptr[u + 1]].tolist())

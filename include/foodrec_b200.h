@@ -1,0 +1,115 @@
+/*
+ * foodrec_b200 -- C ABI of the B200-native graph-propagation + full-ranking hot path.
+ *
+ * The reference (sdu-zyx/Multi-modal-Food-Recommendation, "FoodRec/...") is pure Python and has no
+ * FFI of its own; each entry point below replaces one third-party library op at the call sites
+ * cited (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - the caller owns every buffer, outputs are caller-allocated, nothing is retained after return;
+ *   - `stream` is a `cudaStream_t` passed as `void*`; work is enqueued, never synchronised;
+ *   - return value: 0 on success, negative `FR_E*` otherwise; `fr_last_error()` gives the text;
+ *   - no exceptions, no global state apart from the thread-local error string;
+ *   - dense matrices are fp32 row-major `[rows, d]` with leading dimension `d` (16-byte aligned rows).
+ */
+#ifndef FOODREC_B200_H
+#define FOODREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR_OK 0
+#define FR_EINVAL (-1)       /* bad argument (null pointer, negative extent, misalignment)          */
+#define FR_EUNSUPPORTED (-2) /* shape outside what the kernels are specialised for                  */
+#define FR_ECUDA (-3)        /* CUDA runtime error at launch                                        */
+
+#define FR_SPMM_SEG 128 /* max nnz per propagation segment (see fr_spmm_plan_*) */
+
+int fr_version(void);
+const char *fr_last_error(void);
+/* Number of kernels this library has launched in the calling process (for bench.py's `gpu_launches`). */
+int64_t fr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Propagation: Y = alpha * (S . X) + beta * Z, S in CSR (fp32 values, int32 indices).
+ * Replaces `torch.sparse.mm(S, X)` at FoodRec/models/cikm_model.py:187,199, pricai_modelx.py:183,
+ * 197,211,223, lightgcn.py:139 and, with the fused `+ beta*Z` / `alpha` epilogue, the
+ * `torch.stack(..).mean(1)` layer combine at cikm_model.py:189-190,201-202 (Horner form:
+ * mean_l S^l E0 = (E0 + S(E0 + S(...)))/(L+1)).  The backward of `torch.sparse.mm` w.r.t. X is the
+ * same call on the CSR of S^T (== S for the symmetric normalised adjacencies).
+ *
+ * Rows are processed as SEGMENTS of at most FR_SPMM_SEG nonzeros so that one popular item cannot
+ * serialise a warp; rows longer than a segment are reduced deterministically (fixed order) by the
+ * last segment to finish.  The segment plan is built once per graph:
+ *
+ *   fr_spmm_plan_sizes : from `row_ptr_host` compute n_seg, n_long (rows split in >1 segment),
+ *                        n_part (total segments belonging to long rows).
+ *   fr_spmm_plan_fill  : fill host arrays seg[n_seg*4] (row, start, len, long_id|-1),
+ *                        long_rows[n_long*4] (first_seg, n_parts, part_base, row).
+ *   The caller uploads both, and provides `partial` (n_part * d floats) and `counters` (n_long int32,
+ *   zero-initialised once; the kernel leaves them zero).
+ *
+ * act: 0 = none, 1 = tanh (applied after `+ bias`), bias: optional [d] (NULL = none).
+ * act/bias serve `tanh(GCNConv(x))` at FoodRec/models/schgn.py:29-41 (S = PyG-normalised directed
+ * adjacency incl. self loops, X = lin(x)).
+ * d must be 32, 64 or 128.
+ */
+int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, int64_t *n_seg, int64_t *n_long,
+                       int64_t *n_part);
+int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, int32_t *seg_host, int32_t *long_rows_host);
+int fr_spmm_csr_f32(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                    const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z,
+                    float alpha, float beta, const float *bias, int32_t act, float *Y, float *partial,
+                    int32_t *counters, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused ranking loss on gathered rows: BPR + embedding regulariser, forward and backward.
+ * Replaces the gathers, `torch.mul(..).sum(1)`, `BPRLoss` and `EmbLoss` at
+ * FoodRec/models/cikm_model.py:255-261,267-279, pricai_modelx.py:252-258,266-274,
+ * lightgcn.py:159-175 and FoodRec/common/loss.py:28-34,45-50.
+ *
+ *   mf  = -(1/B) sum_b log(gamma + sigmoid(<E[u_b], E[io+p_b]> - <E[u_b], E[io+n_b]>))
+ *   reg = (1/reg_den) * sum_g sqrt(sum over rows r in group g of |T_g[idx_g[r]]|^2)
+ *
+ * `emb` is the propagated table [n_rows, d] with users first and items from row `item_off`.
+ * Groups: up to FR_MAX_REG_GROUPS (table pointer, int64 index pointer, count) triples; an index
+ * equal to `pad_idx[g]` (>= 0) contributes a zero row (nn.Embedding padding_idx semantics are the
+ * caller's: the padding row is stored as zeros in the reference, so pad handling only matters for
+ * the backward, where that row must receive no gradient).
+ * out[0] = mf, out[1] = reg (un-weighted).  coef[B] receives d mf / d(pos-neg) for the backward,
+ * gnorm[n_groups] the group norms.  `ws` is a zeroed workspace of fr_rank_loss_ws_floats() floats; its ticket word is left zero.
+ */
+#define FR_MAX_REG_GROUPS 6
+/* floats the caller must provide (zero-initialised once) as `ws` of fr_rank_loss_fwd */
+int64_t fr_rank_loss_ws_floats(void);
+int fr_rank_loss_fwd(const float *emb, int32_t d, int64_t item_off, const int64_t *u, const int64_t *p,
+                     const int64_t *n, int32_t B, float gamma, int32_t n_groups,
+                     const float *const *reg_tab_host, const int64_t *const *reg_idx_host,
+                     const int64_t *reg_cnt_host, float reg_den, float *out, float *coef, float *gnorm,
+                     float *ws, void *stream);
+/* d_emb (zero-initialised [n_rows, d] by the caller) += g_mf * d mf/d emb;
+ * d_tab[g] (dense, zero-initialised or accumulating) += g_reg * d reg/d T_g.  g_out = {g_mf, g_reg} on device. */
+int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, const int64_t *u, const int64_t *p,
+                     const int64_t *n, int32_t B, const float *coef, const float *g_out, float *d_emb,
+                     int32_t n_groups, const float *const *reg_tab_host, const int64_t *const *reg_idx_host,
+                     const int64_t *reg_cnt_host, const int64_t *reg_pad_host, float reg_den,
+                     const float *gnorm, float *const *d_tab_host, void *stream);
+
+/* Row gather out[r] = tab[idx[r]] and its adjoint d_tab[idx[r]] += g[r] (fp32 atomics).
+ * Replaces `E[idx]` indexing at pricai_modelx.py:245-247 and the candidate gathers of
+ * `inference_fast` (cikm_model.py:294-302, pricai_modelx.py:278-286). */
+int fr_gather_rows(const float *tab, int32_t d, const int64_t *idx, int64_t n, float *out, void *stream);
+int fr_scatter_add_rows(const float *g, int32_t d, const int64_t *idx, int64_t n, float *d_tab, void *stream);
+/* scores[r] = <U[user[r]], I[item[r]]>  (inference_fast / inference_by_user). */
+int fr_pair_scores(const float *user_tab, const float *item_tab, int32_t d, const int64_t *user,
+                   const int64_t *item, int64_t n, float *scores, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOODREC_B200_H */

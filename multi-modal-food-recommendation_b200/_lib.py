@@ -1,0 +1,74 @@
+"""ctypes binding of `libfoodrec_b200.so` (the C ABI in include/foodrec_b200.h).
+
+The product path has no fallback: if the library is missing this module raises, and every wrapper
+raises `FoodRecError` on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfoodrec_b200.so")
+
+
+class FoodRecError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise FoodRecError(
+            f"{LIB_PATH} is not built: run `make` (or `python -c 'import __graft_entry__ as g; g.build()'`) "
+            "at the repo root. foodrec_b200 has no CPU or eager fallback.")
+    import torch  # noqa: F401  (loads the CUDA runtime the library links against)
+    return C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+
+
+lib = _load()
+
+_p, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+SIGNATURES = {
+    "fr_version": (C.c_int, []),
+    "fr_last_error": (C.c_char_p, []),
+    "fr_launch_count": (_i64, []),
+    "fr_spmm_plan_sizes": (C.c_int, [_p, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "fr_spmm_plan_fill": (C.c_int, [_p, _i32, _p, _p]),
+    "fr_spmm_csr_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i32, _p, _p, _f32, _f32, _p, _i32, _p, _p, _p, _p]),
+    "fr_rank_loss_ws_floats": (_i64, []),
+    "fr_rank_loss_fwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
+    "fr_rank_loss_bwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _f32, _p, _p, _p]),
+    "fr_gather_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
+    "fr_scatter_add_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
+    "fr_pair_scores": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib.fr_last_error().decode("utf-8", "replace")
+        raise FoodRecError(f"{what or 'foodrec_b200'} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / numpy array, or None."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib.fr_launch_count())

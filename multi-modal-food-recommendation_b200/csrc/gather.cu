@@ -1,0 +1,74 @@
+// Row gather / scatter-add / paired dot products on fp32 embedding tables (sm_100a).
+// HBM-bound byte movers: 128-bit accesses, one (sub-)warp per 256-byte row.
+#include "common.cuh"
+
+namespace {
+
+__global__ void gather_rows_kernel(const float *__restrict__ tab, int d4, const int64_t *__restrict__ idx,
+                                   long long n, float *__restrict__ out) {
+    const long long total = n * d4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / d4;
+        const int c = (int)(i - r * d4);
+        reinterpret_cast<float4 *>(out)[i] = fr::ldg_f4(tab + ((size_t)idx[r] * d4 + c) * 4);
+    }
+}
+
+__global__ void scatter_add_rows_kernel(const float *__restrict__ g, int d, const int64_t *__restrict__ idx,
+                                        long long n, float *__restrict__ d_tab) {
+    const long long total = n * d;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / d;
+        const int c = (int)(i - r * d);
+        atomicAdd(d_tab + (size_t)idx[r] * d + c, __ldg(g + i));
+    }
+}
+
+__global__ void pair_scores_kernel(const float *__restrict__ ut, const float *__restrict__ it, int d,
+                                   const int64_t *__restrict__ user, const int64_t *__restrict__ item, long long n,
+                                   float *__restrict__ scores) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    const float *a = ut + (size_t)user[w] * d, *b = it + (size_t)item[w] * d;
+    float s = 0.f;
+    for (int k = lane; k < d; k += 32) s = fmaf(__ldg(a + k), __ldg(b + k), s);
+    s = fr::warp_sum(s);
+    if (lane == 0) scores[w] = s;
+}
+
+int grid1d(long long work, int block) {
+    long long b = (work + block - 1) / block;
+    return (int)std::max<long long>(1, std::min<long long>(b, (long long)fr::num_sms() * 16));
+}
+
+}  // namespace
+
+extern "C" int fr_gather_rows(const float *tab, int32_t d, const int64_t *idx, int64_t n, float *out, void *stream) {
+    FR_REQUIRE(n >= 0 && d > 0 && d % 4 == 0, "fr_gather_rows: n=%lld d=%d (d must be a multiple of 4)", (long long)n, d);
+    if (n == 0) return FR_OK;
+    FR_REQUIRE(tab && idx && out, "fr_gather_rows: null pointer");
+    gather_rows_kernel<<<grid1d(n * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(tab, d / 4, idx, n, out);
+    return fr::check_launch("fr_gather_rows");
+}
+
+extern "C" int fr_scatter_add_rows(const float *g, int32_t d, const int64_t *idx, int64_t n, float *d_tab,
+                                   void *stream) {
+    FR_REQUIRE(n >= 0 && d > 0, "fr_scatter_add_rows: n=%lld d=%d", (long long)n, d);
+    if (n == 0) return FR_OK;
+    FR_REQUIRE(g && idx && d_tab, "fr_scatter_add_rows: null pointer");
+    scatter_add_rows_kernel<<<grid1d(n * d, 256), 256, 0, (cudaStream_t)stream>>>(g, d, idx, n, d_tab);
+    return fr::check_launch("fr_scatter_add_rows");
+}
+
+extern "C" int fr_pair_scores(const float *user_tab, const float *item_tab, int32_t d, const int64_t *user,
+                              const int64_t *item, int64_t n, float *scores, void *stream) {
+    FR_REQUIRE(n >= 0 && d > 0, "fr_pair_scores: n=%lld d=%d", (long long)n, d);
+    if (n == 0) return FR_OK;
+    FR_REQUIRE(user_tab && item_tab && user && item && scores, "fr_pair_scores: null pointer");
+    const long long blocks = (n * 32 + 255) / 256;
+    pair_scores_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(user_tab, item_tab, d, user, item, n, scores);
+    return fr::check_launch("fr_pair_scores");
+}

@@ -1,0 +1,254 @@
+// Normalised-adjacency propagation  Y = alpha * (S . X) + beta * Z  (+ bias, tanh)  on sm_100a.
+//
+// HBM/L2-bound gather-reduce.  Layout: S in CSR (int32 col, fp32 val), X/Z/Y fp32 row-major [N, D].
+// One warp owns one SEGMENT (<= FR_SPMM_SEG nonzeros of one row).  For D = 64 a half-warp reads one
+// 256-byte embedding row as 16 x 128-bit loads, so a warp consumes two nonzeros per step and keeps
+// eight row gathers in flight (4x unrolled).  Column indices / values are fetched 32 at a time with
+// one coalesced load each and broadcast by shuffle.  Rows longer than a segment write per-segment
+// partials; the last segment to arrive (atomic ticket) re-reads them in fixed order, so the result
+// is bit-reproducible run to run.  Algorithmic bytes per launch:
+//   8*nnz + 4*(R+1) + 4*D*C + 4*D*R   (+ 4*D*R when the fused Z stream is used).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <int D>
+struct Shape {
+    static constexpr int LPR = D / 4;    // lanes per embedding row (one float4 each)
+    static constexpr int RPI = 32 / LPR; // rows (nonzeros) a warp consumes per step
+};
+
+template <int D>
+__device__ __forceinline__ float4 reduce_subgroups(float4 a) {
+#pragma unroll
+    for (int o = 16; o >= Shape<D>::LPR; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+        a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+    }
+    return a;
+}
+
+template <int D, int ACT>
+__device__ __forceinline__ void epilogue_store(float4 acc, int row, int off, const float *__restrict__ Z,
+                                               float alpha, float beta, const float *__restrict__ bias,
+                                               float *__restrict__ Y) {
+    float4 y = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+    const size_t o = (size_t)row * D + off;
+    if (Z != nullptr) {
+        const float4 z = fr::ldg_f4(Z + o);
+        y.x = fmaf(beta, z.x, y.x);
+        y.y = fmaf(beta, z.y, y.y);
+        y.z = fmaf(beta, z.z, y.z);
+        y.w = fmaf(beta, z.w, y.w);
+    }
+    if (bias != nullptr) {
+        const float4 b = fr::ldg_f4(bias + off);
+        fr::add4(y, b);
+    }
+    if (ACT == 1) {
+        y.x = tanhf(y.x);
+        y.y = tanhf(y.y);
+        y.z = tanhf(y.z);
+        y.w = tanhf(y.w);
+    }
+    *reinterpret_cast<float4 *>(Y + o) = y;
+}
+
+template <int D, int ACT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+spmm_seg_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
+                const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
+                const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,
+                float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters) {
+    constexpr int LPR = Shape<D>::LPR;
+    constexpr int RPI = Shape<D>::RPI;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_seg) return;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR;
+    const int off = (lane % LPR) * 4;
+    const int4 s = __ldg(seg + w);  // row, start, len, long_id (-1: whole row)
+    const int *__restrict__ cp = col + s.y;
+    const float *__restrict__ vp = val + s.y;
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = 0; base < s.z; base += 32) {
+        const int cnt = min(32, s.z - base);
+        int c = 0;
+        float v = 0.f;
+        if (lane < cnt) {
+            c = __ldg(cp + base + lane);
+            v = __ldg(vp + base + lane);
+        }
+        for (int j = 0; j < cnt; j += 4 * RPI) {
+            float4 x[4];
+            float vv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int e = j + t * RPI + sub;  // < 32 whenever it is < cnt
+                const int cj = __shfl_sync(0xffffffffu, c, e & 31);
+                vv[t] = __shfl_sync(0xffffffffu, v, e & 31);
+                x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < cnt) x[t] = fr::ldg_f4(X + (size_t)cj * D + off);
+                else vv[t] = 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) fr::fma4(acc, vv[t], x[t]);
+        }
+    }
+    acc = reduce_subgroups<D>(acc);
+
+    if (s.w < 0) {
+        if (lane < LPR) epilogue_store<D, ACT>(acc, s.x, off, Z, alpha, beta, bias, Y);
+        return;
+    }
+    // ---- long row: publish the partial, last arriver reduces all partials in fixed order
+    const int4 lr = __ldg(long_rows + s.w);  // first_seg, n_parts, part_base, row
+    const int part = (int)(w - lr.x);
+    if (lane < LPR)
+        __stcg(reinterpret_cast<float4 *>(partial + ((size_t)lr.z + part) * D + off), acc);
+    __threadfence();
+    __syncwarp();
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(counters + s.w, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != lr.y - 1) return;
+    __threadfence();
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = sub; k < lr.y; k += RPI)
+        fr::add4(tot, fr::ldcg_f4(partial + ((size_t)lr.z + k) * D + off));
+    tot = reduce_subgroups<D>(tot);
+    if (lane < LPR) epilogue_store<D, ACT>(tot, lr.w, off, Z, alpha, beta, bias, Y);
+    if (lane == 0) counters[s.w] = 0;  // leave the ticket counter ready for the next launch
+}
+
+template <int D>
+int launch(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val, const float *X,
+           const float *Z, float alpha, float beta, const float *bias, int act, float *Y, float *partial,
+           int *counters, cudaStream_t st) {
+    const long long blocks = (n_seg + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > 0x7fffffffLL) {
+        fr::set_error("fr_spmm_csr_f32: too many segments (%lld)", (long long)n_seg);
+        return FR_EUNSUPPORTED;
+    }
+    dim3 grid((unsigned)blocks), block(kWarpsPerBlock * 32);
+    if (act == 0)
+        spmm_seg_kernel<D, 0><<<grid, block, 0, st>>>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y,
+                                                      partial, counters);
+    else
+        spmm_seg_kernel<D, 1><<<grid, block, 0, st>>>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y,
+                                                      partial, counters);
+    return fr::check_launch("fr_spmm_csr_f32");
+}
+
+struct PlanCounts {
+    int64_t n_seg = 0, n_long = 0, n_part = 0;
+};
+
+PlanCounts count_plan(const int32_t *rp, int32_t n_rows) {
+    PlanCounts c;
+    for (int32_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = (int64_t)rp[r + 1] - rp[r];
+        const int64_t k = deg <= FR_SPMM_SEG ? 1 : (deg + FR_SPMM_SEG - 1) / FR_SPMM_SEG;
+        c.n_seg += k;
+        if (k > 1) {
+            c.n_long += 1;
+            c.n_part += k;
+        }
+    }
+    return c;
+}
+
+}  // namespace
+
+extern "C" int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, int64_t *n_seg, int64_t *n_long,
+                                  int64_t *n_part) {
+    FR_REQUIRE(row_ptr_host && n_seg && n_long && n_part && n_rows >= 0, "fr_spmm_plan_sizes: bad argument");
+    for (int32_t r = 0; r < n_rows; ++r)
+        FR_REQUIRE(row_ptr_host[r + 1] >= row_ptr_host[r], "fr_spmm_plan_sizes: row_ptr not monotone at %d", r);
+    const PlanCounts c = count_plan(row_ptr_host, n_rows);
+    *n_seg = c.n_seg;
+    *n_long = c.n_long;
+    *n_part = c.n_part;
+    return FR_OK;
+}
+
+// Segment order: every long-row segment first (they are the critical path: the last one also
+// performs the reduction), then whole-row segments by descending length (longest-first keeps the
+// tail of the launch short); ties keep row order so neighbouring rows stay neighbours.
+extern "C" int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, int32_t *seg_host,
+                                 int32_t *long_rows_host) {
+    FR_REQUIRE(row_ptr_host && seg_host && n_rows >= 0, "fr_spmm_plan_fill: bad argument");
+    const int32_t *rp = row_ptr_host;
+    int64_t s = 0, nl = 0, pb = 0;
+    for (int32_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = (int64_t)rp[r + 1] - rp[r];
+        if (deg <= FR_SPMM_SEG) continue;
+        FR_REQUIRE(long_rows_host, "fr_spmm_plan_fill: long_rows_host is null but row %d is long", r);
+        const int64_t k = (deg + FR_SPMM_SEG - 1) / FR_SPMM_SEG;
+        int32_t *lr = long_rows_host + 4 * nl;
+        lr[0] = (int32_t)s;
+        lr[1] = (int32_t)k;
+        lr[2] = (int32_t)pb;
+        lr[3] = r;
+        for (int64_t i = 0; i < k; ++i, ++s) {
+            int32_t *q = seg_host + 4 * s;
+            q[0] = r;
+            q[1] = rp[r] + (int32_t)(i * FR_SPMM_SEG);
+            q[2] = (int32_t)std::min<int64_t>(FR_SPMM_SEG, deg - i * FR_SPMM_SEG);
+            q[3] = (int32_t)nl;
+        }
+        pb += k;
+        ++nl;
+    }
+    // counting sort of the remaining rows by descending degree
+    std::vector<int64_t> start(FR_SPMM_SEG + 2, 0);
+    for (int32_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = (int64_t)rp[r + 1] - rp[r];
+        if (deg <= FR_SPMM_SEG) start[FR_SPMM_SEG - deg + 1] += 1;
+    }
+    for (int i = 1; i <= FR_SPMM_SEG + 1; ++i) start[i] += start[i - 1];
+    for (int32_t r = 0; r < n_rows; ++r) {
+        const int64_t deg = (int64_t)rp[r + 1] - rp[r];
+        if (deg > FR_SPMM_SEG) continue;
+        int32_t *q = seg_host + 4 * (s + start[FR_SPMM_SEG - deg]++);
+        q[0] = r;
+        q[1] = rp[r];
+        q[2] = (int32_t)deg;
+        q[3] = -1;
+    }
+    return FR_OK;
+}
+
+extern "C" int fr_spmm_csr_f32(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                               const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z,
+                               float alpha, float beta, const float *bias, int32_t act, float *Y, float *partial,
+                               int32_t *counters, void *stream) {
+    FR_REQUIRE(n_seg >= 0 && n_long >= 0, "fr_spmm_csr_f32: negative extent");
+    if (n_seg == 0) return FR_OK;
+    FR_REQUIRE(seg && X && Y, "fr_spmm_csr_f32: null seg/X/Y");
+    FR_REQUIRE(n_long == 0 || (long_rows && partial && counters), "fr_spmm_csr_f32: long rows need workspace");
+    FR_REQUIRE(act == 0 || act == 1, "fr_spmm_csr_f32: act must be 0 or 1");
+    FR_REQUIRE((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)Z | (uintptr_t)bias | (uintptr_t)partial |
+                 (uintptr_t)seg | (uintptr_t)long_rows) & 15) == 0,
+               "fr_spmm_csr_f32: pointers must be 16-byte aligned");
+    FR_REQUIRE(X != Y, "fr_spmm_csr_f32: in-place propagation is not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int4 *sg = reinterpret_cast<const int4 *>(seg);
+    const int4 *lr = reinterpret_cast<const int4 *>(long_rows);
+    switch (d) {
+        case 32: return launch<32>(sg, n_seg, lr, col_idx, val, X, Z, alpha, beta, bias, act, Y, partial, counters, st);
+        case 64: return launch<64>(sg, n_seg, lr, col_idx, val, X, Z, alpha, beta, bias, act, Y, partial, counters, st);
+        case 128: return launch<128>(sg, n_seg, lr, col_idx, val, X, Z, alpha, beta, bias, act, Y, partial, counters, st);
+        default:
+            fr::set_error("fr_spmm_csr_f32: d=%d unsupported (32, 64, 128)", d);
+            return FR_EUNSUPPORTED;
+    }
+}

@@ -1,0 +1,132 @@
+"""Normalised adjacencies as device-resident CSR + segment plans (built once per model).
+
+Host-side construction is vectorised numpy with the reference's exact arithmetic
+(FoodRec/models/cikm_model.py:108-180; pricai_modelx.py:105-177; lightgcn.py:76-120):
+degree = count of stored entries per row, `d = (deg + 1e-7) ** -0.5` in fp64, value
+`fp32((d[r] * 1.0) * d[c])`.  The reference fills a `dok_matrix` through a python dict and
+multiplies scipy matrices on every model construction; the values produced here are bit-identical
+(tests/test_host_graph.py checks that against the committed goldens).
+
+`PropGraph` holds what `fr_spmm_csr_f32` consumes: `col`/`val` (CSR payload), the segment plan
+(`seg`, `long_rows`) and the long-row workspace.  For the symmetric graphs `graph.T is graph`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SEG = 128  # FR_SPMM_SEG
+
+
+class PropGraph:
+    def __init__(self, row_ptr: np.ndarray, col: np.ndarray, val: np.ndarray, n_cols: int, device,
+                 transpose: "PropGraph | None | str" = None):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        self.n_rows = int(row_ptr.shape[0] - 1)
+        self.n_cols = int(n_cols)
+        self.nnz = int(row_ptr[-1])
+        self.device = torch.device(device)
+        self.row_ptr_host = row_ptr
+        n_seg, n_long, n_part = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib.fr_spmm_plan_sizes(row_ptr.ctypes.data, self.n_rows, C.byref(n_seg), C.byref(n_long),
+                                               C.byref(n_part)), "fr_spmm_plan_sizes")
+        self.n_seg, self.n_long, self.n_part = n_seg.value, n_long.value, n_part.value
+        seg = np.empty((max(self.n_seg, 1), 4), dtype=np.int32)
+        lrows = np.empty((max(self.n_long, 1), 4), dtype=np.int32)
+        _lib.check(_lib.lib.fr_spmm_plan_fill(row_ptr.ctypes.data, self.n_rows, seg.ctypes.data, lrows.ctypes.data),
+                   "fr_spmm_plan_fill")
+        self.seg_host, self.long_rows_host = seg, lrows
+        dev = self.device
+        self.col = torch.from_numpy(np.ascontiguousarray(col, dtype=np.int32)).to(dev)
+        self.val = torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(dev)
+        self.seg = torch.from_numpy(seg).to(dev)
+        self.long_rows = torch.from_numpy(lrows).to(dev)
+        self.counters = torch.zeros(max(self.n_long, 1), dtype=torch.int32, device=dev)
+        self._partial = {}
+        self.T = self if transpose == "self" else transpose
+
+    def partial(self, d: int) -> torch.Tensor:
+        buf = self._partial.get(d)
+        if buf is None:
+            buf = torch.empty(max(self.n_part, 1) * d, dtype=torch.float32, device=self.device)
+            self._partial[d] = buf
+        return buf
+
+    def spmm_bytes(self, d: int, with_z: bool = False) -> int:
+        """Algorithmic bytes of one launch: CSR payload + X read once + Y written once."""
+        b = 8 * self.nnz + 4 * (self.n_rows + 1) + 4 * d * self.n_cols + 4 * d * self.n_rows
+        return b + (4 * d * self.n_rows if with_z else 0)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.val.cpu().numpy(), self.col.cpu().numpy(), self.row_ptr_host),
+                             shape=(self.n_rows, self.n_cols))
+
+
+def _csr_from_pairs(rows: np.ndarray, cols: np.ndarray, n: int):
+    """Sorted, de-duplicated CSR structure of a 0/1 matrix given (row, col) pairs."""
+    key = np.unique(rows.astype(np.int64) * n + cols.astype(np.int64))
+    r = (key // n).astype(np.int64)
+    c = (key % n).astype(np.int32)
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(r, minlength=n), out=row_ptr[1:])
+    return row_ptr, r, c
+
+
+def _sym_norm_values(row_ptr, r, c):
+    deg = np.diff(row_ptr).astype(np.int64) + 1e-7          # (A > 0).sum(axis=1) + 1e-7  -> fp64
+    d = np.power(deg, -0.5)
+    return ((d[r] * np.float64(1.0)) * d[c]).astype(np.float32)  # D * A * D, then FloatTensor cast
+
+
+def symmetric_normalised(rows, cols, n, device) -> PropGraph:
+    """`D^-1/2 (M + M^T) D^-1/2` for the 0/1 pattern M given by (rows, cols)."""
+    rr = np.concatenate([rows, cols])
+    cc = np.concatenate([cols, rows])
+    row_ptr, r, c = _csr_from_pairs(rr, cc, n)
+    if row_ptr[-1] >= 2 ** 31:
+        raise _lib.FoodRecError("graph has >= 2^31 stored entries; int32 CSR offsets would overflow")
+    return PropGraph(row_ptr, c, _sym_norm_values(row_ptr, r, c), n, device, transpose="self")
+
+
+def norm_adj_user_item(train_coo, n_users: int, n_items: int, device) -> PropGraph:
+    """User-item bipartite graph `[[0,R],[R^T,0]]`, normalised.  cikm_model.py:136-180."""
+    u = np.asarray(train_coo.row, dtype=np.int64)
+    i = np.asarray(train_coo.col, dtype=np.int64) + n_users
+    return symmetric_normalised(u, i, n_users + n_items, device)
+
+
+def norm_adj_item_side(triples, n_items: int, n_side: int, device) -> PropGraph:
+    """Item / side-node (ingredient or cluster) graph; `triples[:,0]` item, `triples[:,1]` side id.
+    cikm_model.py:91-134, pricai_modelx.py:88-131."""
+    t = np.asarray(triples, dtype=np.int64)
+    return symmetric_normalised(t[:, 1] + n_items, t[:, 0], n_items + n_side, device)
+
+
+def gcn_normalised(src, dst, n_nodes: int, device) -> PropGraph:
+    """PyG `GCNConv` normalisation of a directed edge list (source -> target) with one unit
+    self-loop per node; duplicates are kept (they add).  Rows of the returned CSR are TARGETS:
+    `out[t] = sum_e w_e x[s_e]`; `.T` is the CSR of the transpose for the backward.
+    Call site FoodRec/models/schgn.py:34,39,139-151,241-250."""
+    src = np.concatenate([np.asarray(src, dtype=np.int64), np.arange(n_nodes, dtype=np.int64)])
+    dst = np.concatenate([np.asarray(dst, dtype=np.int64), np.arange(n_nodes, dtype=np.int64)])
+    deg = np.bincount(dst, minlength=n_nodes).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        dis = np.power(deg, np.float32(-0.5), dtype=np.float32)
+    dis[np.isinf(dis)] = 0.0
+    w = (dis[src] * np.float32(1.0) * dis[dst]).astype(np.float32)
+
+    def build(rows, cols):
+        order = np.lexsort((cols, rows))
+        rp = np.zeros(n_nodes + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=n_nodes), out=rp[1:])
+        return rp, cols[order].astype(np.int32), w[order]
+
+    fwd = PropGraph(*build(dst, src), n_nodes, device)
+    bwd = PropGraph(*build(src, dst), n_nodes, device)
+    fwd.T, bwd.T = bwd, fwd
+    return fwd

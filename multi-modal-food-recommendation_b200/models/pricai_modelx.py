@@ -1,0 +1,122 @@
+"""CLUSSL (`PRICAI_ModelX`) on the B200 kernels -- drop-in for FoodRec/models/pricai_modelx.py.
+
+Same constructor signature, parameter names / shapes / creation order (so a seed gives the same
+initial `state_dict`, and checkpoints interchange), same `forward` / `calculate_loss` /
+`inference_fast` results.  What changed is underneath: the four normalised adjacencies are CSR
+segment plans built once (`graph.py`), each propagation is `L` fused launches
+(`ops.propagate_mean`), and the BPR / regulariser gathers are one fused launch each way.
+Quirks kept on purpose: image/text graphs run `n_ri_layers` layers, `n_mm_layers`
+is read and unused; `proj_*` layers exist but are not applied.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import graph as G
+from .. import ops
+from ..common.init import xavier_uniform_initialization
+from ..common.loss import BPRLoss, EmbLoss
+from ._base import DotProductRecommender
+
+
+class PRICAI_ModelX(DotProductRecommender):
+    def __init__(self, config, dataset):
+        super().__init__(config, dataset)
+        self.config = config
+        self.dataset = dataset
+        self.n_ingredients = dataset.num_ingredients
+        self.n_cal_level = dataset.num_calories_level
+        self.n_health_level = (len(dataset.health_level_multi_hot[0]) if config["use_health_level_multi_hot"]
+                               else dataset.num_health_level)
+        self.interaction_matrix = dataset.train_coo_matrix
+        self.latent_dim = config["embedding_size"]
+        self.n_ri_layers = config["n_ri_layers"]
+        self.n_mm_layers = config["n_mm_layers"]
+        self.n_ui_layers = config["n_ui_layers"]
+        self.reg_weight = config["reg_weight"]
+        self.loss_cl = config["loss_cl"]
+        self.knn_k = config["knn_k"]
+        self.mm_image_weight = config["mm_image_weight"]
+        self.n_cluster = config["n_cluster"]
+
+        self.user_embedding = nn.Embedding(self.n_users, self.latent_dim)
+        self.item_embedding = nn.Embedding(self.n_items, self.latent_dim)
+        self.ingre_embedding = nn.Embedding(self.n_ingredients + 1, self.latent_dim, padding_idx=self.n_ingredients)
+        self.mf_loss = BPRLoss()
+        self.reg_loss = EmbLoss()
+
+        dev = self.device
+        self.g_ui = G.norm_adj_user_item(self.interaction_matrix, self.n_users, self.n_items, dev)
+        self.g_image = G.norm_adj_item_side(dataset.image_cluster_triples, self.n_items, self.n_cluster, dev)
+        self.g_text = G.norm_adj_item_side(dataset.text_cluster_triples, self.n_items, self.n_cluster, dev)
+        self.g_ingre = G.norm_adj_item_side(dataset.rIngre_triples, self.n_items, self.n_ingredients, dev)
+
+        self.proj_ingre = nn.Linear(self.latent_dim, self.latent_dim)
+        self.proj_text = nn.Linear(self.latent_dim, self.latent_dim)
+        self.proj_image = nn.Linear(self.latent_dim, self.latent_dim)
+        self.image_prototype_embedding = nn.Embedding(self.n_cluster, self.latent_dim)
+        self.text_prototype_embedding = nn.Embedding(self.n_cluster, self.latent_dim)
+        self.apply(xavier_uniform_initialization)
+
+        self.v_center = self.t_center = None
+        if config["use_center_embedding"]:
+            root = config["interaction_data_path"]
+            self.v_center = torch.tensor(np.load(root + "mm_cluster/image_center.npy").astype(np.float32)).to(dev)
+            self.t_center = torch.tensor(np.load(root + "mm_cluster/text_center.npy").astype(np.float32)).to(dev)
+        if self.v_center is not None:
+            self.image_prototype_embedding = nn.Embedding.from_pretrained(self.v_center, freeze=False)
+            self.image_trs = nn.Linear(self.v_center.shape[1], self.latent_dim)
+            nn.init.xavier_normal_(self.image_trs.weight)
+        if self.t_center is not None:
+            self.text_prototype_embedding = nn.Embedding.from_pretrained(self.t_center, freeze=False)
+            self.text_trs = nn.Linear(self.t_center.shape[1], self.latent_dim)
+            nn.init.xavier_normal_(self.text_trs.weight)
+
+    # ------------------------------------------------------------------ propagation
+    def _propagate_all(self):
+        I = self.n_items
+        item_w = self.item_embedding.weight
+        ing = ops.propagate_mean(self.g_ingre, torch.cat((item_w, self.ingre_embedding.weight[:-1]), 0),
+                                 self.n_ri_layers)
+        image_proto = self.image_prototype_embedding.weight
+        if self.v_center is not None:
+            image_proto = self.image_trs(image_proto)
+        img = ops.propagate_mean(self.g_image, torch.cat((item_w, image_proto), 0), self.n_ri_layers)
+        text_proto = self.text_prototype_embedding.weight
+        if self.t_center is not None:
+            text_proto = self.text_trs(text_proto)
+        txt = ops.propagate_mean(self.g_text, torch.cat((item_w, text_proto), 0), self.n_ri_layers)
+        item_emb = ing[:I] + img[:I] + txt[:I]
+        all_emb = ops.propagate_mean(self.g_ui, torch.cat((self.user_embedding.weight, item_emb), 0),
+                                     self.n_ui_layers)
+        return all_emb, (img, txt, ing)
+
+    def forward(self):
+        all_emb, (img, txt, ing) = self._propagate_all()
+        I = self.n_items
+        return all_emb[:self.n_users], all_emb[self.n_users:], (img[:I], txt[:I], ing[:I])
+
+    # ------------------------------------------------------------------ training loss
+    def calculate_loss(self, batch_data):
+        user, pos_item, neg_item = batch_data["u_id"], batch_data["pos_i_id"], batch_data["neg_i_id"]
+        all_item = torch.cat([pos_item, neg_item], dim=0)
+        all_emb, (img, txt, ing) = self._propagate_all()
+        item_image = ops.gather_rows(img, all_item)   # rows < n_items of the [I + C, d] tables
+        item_text = ops.gather_rows(txt, all_item)
+        item_ingre = ops.gather_rows(ing, all_item)
+        uw, iw = self.user_embedding.weight, self.item_embedding.weight
+        mf_loss_g, reg = ops.rank_loss(all_emb, self.n_users, user, pos_item, neg_item,
+                                       [(uw, user), (iw, pos_item), (iw, neg_item)],
+                                       reg_den=float(neg_item.shape[0]), gamma=self.mf_loss.gamma)
+        cl_loss = (ops.correlation_distance(item_image, item_text)
+                   + ops.correlation_distance(item_image, item_ingre)
+                   + ops.correlation_distance(item_ingre, item_text))
+        return mf_loss_g, self.loss_cl * cl_loss, (self.reg_weight * reg).reshape(1)
+
+    def CL_loss(self, hidden, hidden_norm=True, temperature=0.5):
+        return ops.info_nce(hidden, temperature=temperature, hidden_norm=hidden_norm)
+
+    def correlation_distance(self, x, y):
+        return ops.correlation_distance(x, y)

@@ -1,0 +1,247 @@
+"""Differentiable operators over the C ABI (raw device pointers in, no torch types cross the boundary).
+
+Each op launches the hand-written sm_100a kernels on torch's current CUDA stream, so they compose
+with autograd, CUDA graphs and `torch.distributed` like any other op.  Nothing here computes on
+the host and nothing falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .graph import PropGraph
+
+_L = _lib.lib
+
+
+def _chk_f32(t: torch.Tensor, name: str):
+    if t.device.type != "cuda":
+        raise _lib.FoodRecError(f"{name} must be a CUDA tensor (foodrec_b200 has no CPU path), got {t.device}")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise _lib.FoodRecError(f"{name} must be contiguous float32, got {t.dtype} contiguous={t.is_contiguous()}")
+
+
+def _idx(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.device.type != "cuda":
+        raise _lib.FoodRecError(f"{name} must be a CUDA tensor, got {t.device}")
+    return t.contiguous() if t.dtype == torch.int64 else t.to(torch.int64).contiguous()
+
+
+# ------------------------------------------------------------------------------------ propagation
+def spmm(graph: PropGraph, X: torch.Tensor, Z: torch.Tensor | None = None, alpha: float = 1.0, beta: float = 0.0,
+         bias: torch.Tensor | None = None, act: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """`out = act(alpha * S @ X + beta * Z + bias)`; no autograd."""
+    _chk_f32(X, "X")
+    if X.shape[0] != graph.n_cols:
+        raise _lib.FoodRecError(f"X has {X.shape[0]} rows, graph has {graph.n_cols} columns")
+    d = X.shape[1]
+    if out is None:
+        out = torch.empty((graph.n_rows, d), dtype=torch.float32, device=X.device)
+    if Z is not None:
+        _chk_f32(Z, "Z")
+    if bias is not None:
+        _chk_f32(bias, "bias")
+    _lib.check(_L.fr_spmm_csr_f32(
+        graph.seg.data_ptr(), graph.n_seg, graph.long_rows.data_ptr(), graph.n_long, graph.col.data_ptr(),
+        graph.val.data_ptr(), d, X.data_ptr(), _lib.ptr(Z), float(alpha), float(beta), _lib.ptr(bias), int(act),
+        out.data_ptr(), graph.partial(d).data_ptr(), graph.counters.data_ptr(), _lib.stream_ptr()),
+        "fr_spmm_csr_f32")
+    return out
+
+
+def propagate_mean_raw(graph: PropGraph, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
+    """`mean_{l=0..L} S^l ego` in Horner form, L fused launches, no layer stack in memory."""
+    if n_layers == 0:
+        return ego.clone()
+    inv = 1.0 / (n_layers + 1)
+    t = ego
+    for layer in range(n_layers):
+        last = layer == n_layers - 1
+        t = spmm(graph, t, Z=ego, alpha=inv if last else 1.0, beta=inv if last else 1.0)
+    return t
+
+
+class _PropagateMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ego, graph, n_layers):
+        ctx.graph, ctx.n_layers = graph, n_layers
+        return propagate_mean_raw(graph, ego.contiguous(), n_layers)
+
+    @staticmethod
+    def backward(ctx, g):
+        # d/d ego of mean_l S^l ego is mean_l (S^T)^l g: the same Horner recurrence on S^T
+        gt = ctx.graph.T
+        if gt is None:
+            raise _lib.FoodRecError("graph has no transpose plan; build it with a `.T`")
+        return propagate_mean_raw(gt, g.contiguous(), ctx.n_layers), None, None
+
+
+def propagate_mean(graph: PropGraph, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
+    """Differentiable layer-mean propagation (replaces the `torch.sparse.mm` loop + stack/mean)."""
+    return _PropagateMean.apply(ego, graph, n_layers)
+
+
+class _SpmmBiasTanh(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, graph):
+        y = spmm(graph, x.contiguous(), bias=bias.contiguous(), act=1)
+        ctx.save_for_backward(y)
+        ctx.graph = graph
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        dpre = (g * (1.0 - y * y)).contiguous()
+        return spmm(ctx.graph.T, dpre), dpre.sum(0), None
+
+
+def gcn_propagate_tanh(graph: PropGraph, h: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """`tanh(S @ h + bias)` -- the propagate/bias/tanh part of SCHGN's GraphConv (schgn.py:38-41)."""
+    return _SpmmBiasTanh.apply(h, bias, graph)
+
+
+# ---------------------------------------------------------------------------------- ranking loss
+_WS = {}
+
+
+def _workspace(device) -> torch.Tensor:
+    ws = _WS.get(device)
+    if ws is None:
+        ws = torch.zeros(int(_L.fr_rank_loss_ws_floats()), dtype=torch.float32, device=device)
+        _WS[device] = ws
+    return ws
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * max(len(tensors), 1))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+class _RankLoss(torch.autograd.Function):
+    """(mf_loss, reg_loss) = BPR on propagated rows + EmbLoss on ego rows, one launch each way."""
+
+    @staticmethod
+    def forward(ctx, emb, item_off, u, p, n, gamma, reg_den, reg_idx, reg_pad, *reg_tabs):
+        _chk_f32(emb, "emb")
+        B, d = u.numel(), emb.shape[1]
+        for t in reg_tabs:
+            _chk_f32(t, "regulariser table")
+            if t.shape[1] != d:
+                raise _lib.FoodRecError("regulariser tables must share the embedding width")
+        dev = emb.device
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        coef = torch.empty(B, dtype=torch.float32, device=dev)
+        gnorm = torch.empty(max(len(reg_tabs), 1), dtype=torch.float32, device=dev)
+        cnt = (C.c_int64 * max(len(reg_tabs), 1))(*[int(i.numel()) for i in reg_idx])
+        _lib.check(_L.fr_rank_loss_fwd(
+            emb.data_ptr(), d, int(item_off), u.data_ptr(), p.data_ptr(), n.data_ptr(), B, float(gamma),
+            len(reg_tabs), _ptr_array(reg_tabs), _ptr_array(reg_idx), cnt, float(reg_den), out.data_ptr(),
+            coef.data_ptr(), gnorm.data_ptr(), _workspace(dev).data_ptr(), _lib.stream_ptr()), "fr_rank_loss_fwd")
+        ctx.save_for_backward(emb, u, p, n, coef, gnorm, *reg_idx, *reg_tabs)
+        ctx.meta = (int(item_off), float(reg_den), len(reg_tabs), tuple(int(x) for x in reg_pad))
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_mf, g_reg):
+        item_off, reg_den, ng, pads = ctx.meta
+        emb, u, p, n, coef, gnorm = ctx.saved_tensors[:6]
+        reg_idx = ctx.saved_tensors[6:6 + ng]
+        reg_tabs = ctx.saved_tensors[6 + ng:6 + 2 * ng]
+        B, d = u.numel(), emb.shape[1]
+        g_out = torch.stack([g_mf.reshape(()), g_reg.reshape(())]).to(torch.float32).contiguous()
+        d_emb = torch.zeros_like(emb) if ctx.needs_input_grad[0] else None
+        # one dense gradient per distinct table (the same table may back several groups)
+        uniq, d_tabs = {}, []
+        for k, t in enumerate(reg_tabs):
+            if not ctx.needs_input_grad[9 + k]:
+                d_tabs.append(None)
+                continue
+            key = t.data_ptr()
+            if key not in uniq:
+                uniq[key] = torch.zeros_like(t)
+            d_tabs.append(uniq[key])
+        cnt = (C.c_int64 * max(ng, 1))(*[int(i.numel()) for i in reg_idx])
+        pad = (C.c_int64 * max(ng, 1))(*pads)
+        _lib.check(_L.fr_rank_loss_bwd(
+            emb.data_ptr(), d, item_off, u.data_ptr(), p.data_ptr(), n.data_ptr(), B, coef.data_ptr(),
+            g_out.data_ptr(), _lib.ptr(d_emb), ng, _ptr_array(reg_tabs), _ptr_array(reg_idx), cnt, pad, reg_den,
+            gnorm.data_ptr(), _ptr_array(d_tabs), _lib.stream_ptr()), "fr_rank_loss_bwd")
+        # a table shared by several groups gets its (already summed) gradient once
+        seen, grads = set(), []
+        for k, t in enumerate(reg_tabs):
+            if d_tabs[k] is None or t.data_ptr() in seen:
+                grads.append(None)
+            else:
+                seen.add(t.data_ptr())
+                grads.append(d_tabs[k])
+        return (d_emb, None, None, None, None, None, None, None, None, *grads)
+
+
+def rank_loss(emb: torch.Tensor, item_off: int, u, p, n, reg_groups, reg_den: float, gamma: float = 1e-10):
+    """BPR over rows of `emb` (users at `u`, items at `item_off + p/n`) and the un-weighted EmbLoss
+    `sum_g ||T_g[idx_g]||_F / reg_den` over `reg_groups = [(table, idx, pad_idx|-1), ...]`.
+    Returns two 0-dim tensors `(mf_loss, reg_loss)`."""
+    u, p, n = _idx(u, "u"), _idx(p, "p"), _idx(n, "n")
+    tabs = [g[0] for g in reg_groups]
+    idxs = [_idx(g[1].reshape(-1), "reg idx") for g in reg_groups]
+    pads = [(-1 if (len(g) < 3 or g[2] is None) else int(g[2])) for g in reg_groups]
+    return _RankLoss.apply(emb, item_off, u, p, n, gamma, reg_den, idxs, pads, *tabs)
+
+
+# ------------------------------------------------------------------------------- gathers / scores
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tab, idx):
+        _chk_f32(tab, "table")
+        out = torch.empty((idx.numel(), tab.shape[1]), dtype=torch.float32, device=tab.device)
+        _lib.check(_L.fr_gather_rows(tab.data_ptr(), tab.shape[1], idx.data_ptr(), idx.numel(), out.data_ptr(),
+                                     _lib.stream_ptr()), "fr_gather_rows")
+        ctx.save_for_backward(idx)
+        ctx.shape = tab.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        d_tab = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        g = g.contiguous()
+        _lib.check(_L.fr_scatter_add_rows(g.data_ptr(), g.shape[1], idx.data_ptr(), idx.numel(), d_tab.data_ptr(),
+                                          _lib.stream_ptr()), "fr_scatter_add_rows")
+        return d_tab, None
+
+
+def gather_rows(tab: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """`tab[idx]` with a scatter-add backward."""
+    return _GatherRows.apply(tab.contiguous(), _idx(idx, "idx"))
+
+
+def pair_scores(user_tab: torch.Tensor, item_tab: torch.Tensor, user: torch.Tensor, item: torch.Tensor):
+    """`(user_tab[user] * item_tab[item]).sum(1)` (inference_fast / inference_by_user); no autograd."""
+    user_tab, item_tab = user_tab.detach(), item_tab.detach()
+    if not user_tab.is_contiguous():
+        user_tab = user_tab.contiguous()
+    if not item_tab.is_contiguous():
+        item_tab = item_tab.contiguous()
+    _chk_f32(user_tab, "user table")
+    _chk_f32(item_tab, "item table")
+    user, item = _idx(user, "user"), _idx(item, "item")
+    out = torch.empty(user.numel(), dtype=torch.float32, device=user_tab.device)
+    _lib.check(_L.fr_pair_scores(user_tab.data_ptr(), item_tab.data_ptr(), user_tab.shape[1], user.data_ptr(),
+                                 item.data_ptr(), user.numel(), out.data_ptr(), _lib.stream_ptr()), "fr_pair_scores")
+    return out
+
+
+# --------------------------------------------------------------------------- contrastive terms
+def correlation_distance(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Distance correlation of two `[n, d]` views (FoodRec/models/pricai_modelx.py:409-437);
+    returns shape `[1]` like the reference."""
+    from . import contrastive
+    return contrastive.correlation_distance(x, y)
+
+
+def info_nce(hidden: torch.Tensor, temperature: float = 0.5, hidden_norm: bool = True) -> torch.Tensor:
+    """SimCLR NT-Xent over the two halves of `hidden` (`CL_loss`, pricai_modelx.py:354-378)."""
+    from . import contrastive
+    return contrastive.info_nce(hidden, temperature, hidden_norm)

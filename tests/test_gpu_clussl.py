@@ -1,0 +1,94 @@
+"""GPU parity of the CLUSSL drop-in (`PRICAI_ModelX`) against reference goldens and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+class Cfg(dict):
+    def __getitem__(self, k):
+        return self.get(k)
+
+
+def cfg_for(ds, **kw):
+    base = dict(device="cuda", embedding_size=64, train_batch_size=64, is_multimodal_model=True, end2end=False,
+                use_health_level_multi_hot=True, n_ri_layers=2, n_mm_layers=1, n_ui_layers=1, reg_weight=0.01,
+                loss_cl=0.1, n_cluster=ds.cfg.n_cluster)
+    base.update(kw)
+    return Cfg(base)
+
+
+def close(a, b, rtol=1e-5, atol=0.0):
+    a = np.asarray(a.detach().cpu() if torch.is_tensor(a) else a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(np.abs(b).max(), 1e-30)
+    err = np.abs(a - b).max()
+    assert err <= rtol * scale + atol, (err, scale)
+
+
+def dev_batch(batch):
+    return {k: torch.from_numpy(np.asarray(v)).cuda() for k, v in batch.items()}
+
+
+def test_clussl_matches_reference_golden(mini_ds, mini_batches):
+    from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
+    g = load_golden("clussl_mini.npz")
+    torch.manual_seed(999)
+    m = PRICAI_ModelX(cfg_for(mini_ds), mini_ds)
+    m.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")})
+    m = m.to("cuda")
+    ua, ia, (vi, vt, vg) = m.forward()
+    for got, key in ((ua, "user_all"), (ia, "item_all"), (vi, "item_image"), (vt, "item_text"), (vg, "item_ingre")):
+        close(got, g["fwd/" + key])
+    for b, batch in enumerate(mini_batches):
+        m.zero_grad()
+        losses = m.calculate_loss(dev_batch(batch))
+        close(torch.stack([x.reshape(()) for x in losses]), g[f"loss/{b}"])
+        sum(losses).backward()
+        for name, p in m.named_parameters():
+            key = f"grad/{name}/{b}"
+            if key in g:
+                # distance-correlation backward is ill-conditioned in fp32 (see test_oracle_golden.py)
+                close(p.grad, g[key], rtol=5e-4)
+    cand = torch.from_numpy(g["infer/cand"]).cuda()
+    sc = m.inference_fast({"user_input": torch.full_like(cand, 3), "item_input": cand}, ua, ia)
+    close(sc, g["infer/scores"])
+
+
+def test_clussl_c1_vs_oracle():
+    from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
+    from foodrec_b200.synth import make_dataset, sample_train_batches
+    from oracle import adjacency, losses, propagation
+    ds = make_dataset("C1")
+    torch.manual_seed(999)
+    m = PRICAI_ModelX(cfg_for(ds, train_batch_size=512), ds)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to("cuda")
+    P = {k: sd[k].clone().requires_grad_(True) for k in (
+        "user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight",
+        "image_prototype_embedding.weight", "text_prototype_embedding.weight")}
+    S_ui = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    S_g = adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients)
+    S_v = adjacency.norm_adj_item_side(ds.image_cluster_triples, ds.n_items, ds.cfg.n_cluster)
+    S_t = adjacency.norm_adj_item_side(ds.text_cluster_triples, ds.n_items, ds.cfg.n_cluster)
+    out = propagation.clussl_forward(S_ui, S_g, S_v, S_t, P["user_embedding.weight"], P["item_embedding.weight"],
+                                     P["ingre_embedding.weight"], P["image_prototype_embedding.weight"],
+                                     P["text_prototype_embedding.weight"], ds.n_users, ds.n_items,
+                                     ds.num_ingredients, ds.cfg.n_cluster, 2, 1)
+    batch = sample_train_batches(ds, 512, 1, seed=3)[0]
+    u, p, n = (torch.from_numpy(batch[k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+    terms = losses.clussl_loss(out, P["user_embedding.weight"], P["item_embedding.weight"], u, p, n, 0.01, 0.1)
+    sum(terms).sum().backward()
+    got = m.calculate_loss(dev_batch(batch))
+    close(torch.stack([x.reshape(()) for x in got]), [float(t) for t in terms])
+    sum(got).backward()
+    ua, ia, _ = m.forward()
+    close(ua, out[0].detach().numpy())
+    close(ia, out[1].detach().numpy())
+    for name, p_ in m.named_parameters():
+        if name in P:
+            close(p_.grad, P[name].grad.numpy(), rtol=5e-4)

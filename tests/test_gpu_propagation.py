@@ -1,0 +1,130 @@
+"""GPU parity: propagation kernel (through the C ABI) vs the CPU oracle's `torch.sparse.mm`."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star: embeddings within 1e-5 relative in fp32
+
+
+def close(a, b, rtol=RTOL):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape
+    scale = max(float(b.abs().max()), 1e-30)
+    err = float((a - b).abs().max())
+    assert err <= rtol * scale, (err, scale)
+
+
+def random_csr(n_rows, n_cols, degs, seed):
+    rng = np.random.default_rng(seed)
+    rp = np.concatenate([[0], np.cumsum(degs)]).astype(np.int64)
+    col = np.concatenate([np.sort(rng.choice(n_cols, size=d, replace=d > n_cols)) for d in degs] + [np.zeros(0, int)])
+    val = rng.standard_normal(int(rp[-1])).astype(np.float32)
+    return rp, col.astype(np.int32), val
+
+
+def to_torch_sparse(rp, col, val, n_rows, n_cols):
+    rows = np.repeat(np.arange(n_rows), np.diff(rp))
+    return torch.sparse_coo_tensor(torch.from_numpy(np.stack([rows, col.astype(np.int64)])), torch.from_numpy(val),
+                                   (n_rows, n_cols))
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+@pytest.mark.parametrize("case", ["ragged", "long", "empty", "single"])
+def test_spmm_matches_sparse_mm(d, case):
+    from foodrec_b200 import graph as G, ops
+    rng = np.random.default_rng(1)
+    n_cols = 3000
+    if case == "ragged":
+        degs = rng.integers(0, 40, size=2000)
+    elif case == "long":  # rows far beyond one segment, incl. exact multiples of the segment length
+        degs = np.array([5000, 128, 129, 256, 0, 1, 2999, 127, 640] + list(rng.integers(0, 300, size=300)))
+    elif case == "empty":
+        degs = np.zeros(257, dtype=np.int64)
+    else:
+        degs = np.array([1])
+    rp, col, val = random_csr(len(degs), n_cols, degs, 2)
+    g = G.PropGraph(rp, col, val, n_cols, "cuda")
+    X = torch.randn(n_cols, d)
+    Z = torch.randn(len(degs), d)
+    bias = torch.randn(d)
+    S = to_torch_sparse(rp, col, val, len(degs), n_cols)
+    ref = torch.sparse.mm(S, X)
+    close(ops.spmm(g, X.cuda()), ref)
+    close(ops.spmm(g, X.cuda(), Z=Z.cuda(), alpha=0.25, beta=0.5), 0.25 * ref + 0.5 * Z)
+    close(ops.spmm(g, X.cuda(), bias=bias.cuda(), act=1), torch.tanh(ref + bias))
+    # bit-reproducible (long rows are reduced in fixed order, not by arrival)
+    a, b = ops.spmm(g, X.cuda()), ops.spmm(g, X.cuda())
+    assert torch.equal(a, b)
+    assert int(g.counters.abs().sum()) == 0
+
+
+def test_rejects_bad_arguments():
+    from foodrec_b200 import _lib, graph as G, ops
+    rp, col, val = random_csr(4, 10, [1, 2, 0, 3], 0)
+    g = G.PropGraph(rp, col, val, 10, "cuda")
+    with pytest.raises(_lib.FoodRecError):
+        ops.spmm(g, torch.randn(10, 48).cuda())           # unsupported width
+    with pytest.raises(_lib.FoodRecError):
+        ops.spmm(g, torch.randn(9, 64).cuda())            # wrong row count
+    with pytest.raises(_lib.FoodRecError):
+        ops.spmm(g, torch.randn(10, 64))                  # CPU tensor: no fallback
+    with pytest.raises(_lib.FoodRecError):
+        ops.spmm(g, torch.randn(10, 64).cuda().double())  # dtype
+
+
+@pytest.mark.parametrize("layers", [0, 1, 2, 3])
+def test_layer_mean_propagation_fwd_bwd(mini_ds, layers):
+    from foodrec_b200 import graph as G, ops
+    from oracle import adjacency, propagation
+    ds = mini_ds
+    S = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    g = G.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items, "cuda")
+    torch.manual_seed(0)
+    ego = (torch.randn(ds.n_users + ds.n_items, 64) * 0.1).requires_grad_(True)
+    w = torch.randn(ds.n_users + ds.n_items, 64)
+    ref = propagation.layer_mean_propagate(S, ego, layers)
+    (ref * w).sum().backward()
+    ego_d = ego.detach().cuda().requires_grad_(True)
+    out = ops.propagate_mean(g, ego_d, layers)
+    (out * w.cuda()).sum().backward()
+    close(out, ref)
+    close(ego_d.grad, ego.grad)
+
+
+def test_directed_gcn_propagation_fwd_bwd(mini_ds):
+    from foodrec_b200 import graph as G, ops
+    from oracle import adjacency, propagation
+    ds = mini_ds
+    n = ds.n_users + ds.n_items + ds.num_ingredients + ds.num_calories_level
+    ei = adjacency.schgn_edge_index(ds)
+    src, dst, w = adjacency.gcn_norm_edges(ei, n)
+    g = G.gcn_normalised(ei[0].numpy(), ei[1].numpy(), n, "cuda")
+    torch.manual_seed(1)
+    x = (torch.randn(n, 64) * 0.3).requires_grad_(True)
+    W = (torch.randn(64, 64) * 0.2).requires_grad_(True)
+    b = (torch.randn(64) * 0.1).requires_grad_(True)
+    t = torch.randn(n, 64)
+    ref = propagation.gcn_conv_tanh(x, src, dst, w, W, b)
+    (ref * t).sum().backward()
+    xd, Wd, bd = (v.detach().cuda().requires_grad_(True) for v in (x, W, b))
+    out = ops.gcn_propagate_tanh(g, xd @ Wd.t(), bd)
+    (out * t.cuda()).sum().backward()
+    close(out, ref)
+    close(xd.grad, x.grad, 2e-5)
+    close(Wd.grad, W.grad, 2e-5)
+    close(bd.grad, b.grad, 2e-5)
+
+
+def test_c1_scale_forward_vs_oracle():
+    from foodrec_b200 import graph as G, ops
+    from foodrec_b200.synth import make_dataset
+    from oracle import adjacency, propagation
+    ds = make_dataset("C1", features=False)
+    S = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    g = G.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items, "cuda")
+    assert g.n_long > 0  # popular items exceed one segment at this scale
+    torch.manual_seed(0)
+    ego = torch.randn(ds.n_users + ds.n_items, 64) * 0.1
+    close(ops.propagate_mean(g, ego.cuda(), 2), propagation.layer_mean_propagate(S, ego, 2))

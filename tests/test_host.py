@@ -1,0 +1,119 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol,
+the graph builder reproduces the reference's adjacency bit for bit, segment plans are well formed,
+and the drop-in models initialise to the reference's `state_dict` under the same seed."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+import foodrec_b200  # noqa: F401
+from foodrec_b200 import _lib, graph as G
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "foodrec_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(fr_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(_lib.lib, n), f"libfoodrec_b200.so does not export {n}"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    assert _lib.lib.fr_version() >= 100
+
+
+def test_error_reporting_without_gpu():
+    import ctypes as C
+    rp = np.array([0, 3, 2], dtype=np.int32)  # not monotone
+    a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = _lib.lib.fr_spmm_plan_sizes(rp.ctypes.data, 2, C.byref(a), C.byref(b), C.byref(c))
+    assert rc == -1
+    assert b"monotone" in _lib.lib.fr_last_error()
+    with pytest.raises(_lib.FoodRecError):
+        _lib.check(rc, "plan")
+
+
+def _csr_matches(g, idx, val):
+    rows = np.repeat(np.arange(g.n_rows), np.diff(g.row_ptr_host))
+    order = np.lexsort((idx[1], idx[0]))
+    assert np.array_equal(rows, idx[0][order])
+    assert np.array_equal(g.col.numpy().astype(np.int64), idx[1][order])
+    assert np.array_equal(g.val.numpy(), val[order])  # bit-exact fp32
+
+
+def test_graph_builder_bit_exact_vs_reference(mini_ds):
+    ds, g = mini_ds, load_golden("clussl_mini.npz")
+    _csr_matches(G.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items, "cpu"),
+                 g["adj/norm_adj_matrix/idx"], g["adj/norm_adj_matrix/val"])
+    _csr_matches(G.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients, "cpu"),
+                 g["adj/ingre_norm_adj/idx"], g["adj/ingre_norm_adj/val"])
+    _csr_matches(G.norm_adj_item_side(ds.image_cluster_triples, ds.n_items, ds.cfg.n_cluster, "cpu"),
+                 g["adj/image_norm_adj/idx"], g["adj/image_norm_adj/val"])
+    _csr_matches(G.norm_adj_item_side(ds.text_cluster_triples, ds.n_items, ds.cfg.n_cluster, "cpu"),
+                 g["adj/text_norm_adj/idx"], g["adj/text_norm_adj/val"])
+
+
+@pytest.mark.parametrize("degs", [[0, 1, 128, 129, 0, 1000, 5, 256, 0], [], [0, 0], [4000]])
+def test_segment_plan_covers_every_nonzero_once(degs):
+    rp = np.concatenate([[0], np.cumsum(degs)]).astype(np.int32)
+    g = G.PropGraph(rp, np.zeros(rp[-1], np.int32), np.ones(rp[-1], np.float32), max(len(degs), 1), "cpu")
+    seg = g.seg_host[:g.n_seg]
+    assert g.n_seg == sum(max(1, -(-d // G.SEG)) for d in degs)
+    seen = np.zeros(int(rp[-1]), dtype=np.int32)
+    rows_seen = set()
+    for r, s, l, lid in seg:
+        assert 0 <= l <= G.SEG and rp[r] <= s and s + l <= rp[r + 1]
+        seen[s:s + l] += 1
+        rows_seen.add(int(r))
+        assert (lid >= 0) == (degs[r] > G.SEG)
+    assert (seen == 1).all() and rows_seen == set(range(len(degs)))
+    lr = g.long_rows_host[:g.n_long]
+    assert g.n_long == sum(d > G.SEG for d in degs)
+    assert g.n_part == sum(-(-d // G.SEG) for d in degs if d > G.SEG)
+    for k, (first, nparts, pbase, row) in enumerate(lr):
+        assert (seg[first:first + nparts, 0] == row).all() and (seg[first:first + nparts, 3] == k).all()
+    # whole-row segments come sorted by descending length
+    single = seg[seg[:, 3] < 0][:, 2]
+    assert (np.diff(single) <= 0).all()
+
+
+def test_gcn_normalisation_matches_oracle(mini_ds):
+    from oracle import adjacency
+    ei = adjacency.schgn_edge_index(mini_ds)
+    n = mini_ds.n_users + mini_ds.n_items + mini_ds.num_ingredients + mini_ds.num_calories_level
+    src, dst, w = adjacency.gcn_norm_edges(ei, n)
+    g = G.gcn_normalised(ei[0].numpy(), ei[1].numpy(), n, "cpu")
+    import scipy.sparse as sp
+    ref = sp.coo_matrix((w.numpy(), (dst.numpy(), src.numpy())), shape=(n, n)).tocsr()
+    ref.sum_duplicates()
+    got = g.to_scipy()
+    got.sum_duplicates()
+    assert abs(got - ref).max() < 1e-7
+    assert abs(g.T.to_scipy() - ref.T).max() < 1e-7
+
+
+class Cfg(dict):
+    def __getitem__(self, k):
+        return self.get(k)
+
+
+BASE = dict(device="cpu", embedding_size=64, train_batch_size=64, is_multimodal_model=True, end2end=False,
+            use_health_level_multi_hot=True, num_attention_heads=2, num_hidden_layers=2,
+            attention_probs_dropout_prob=0.0, hidden_act="gelu")
+
+
+def test_clussl_same_seed_same_state_dict(mini_ds):
+    from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
+    g = load_golden("clussl_mini.npz")
+    cfg = Cfg({**BASE, "n_ri_layers": 2, "n_mm_layers": 1, "n_ui_layers": 1, "reg_weight": 0.01, "loss_cl": 0.1,
+               "n_cluster": mini_ds.cfg.n_cluster})
+    torch.manual_seed(999)
+    m = PRICAI_ModelX(cfg, mini_ds)
+    sd = m.state_dict()
+    ref_keys = sorted(k[3:] for k in g if k.startswith("sd/"))
+    assert sorted(sd.keys()) == ref_keys
+    for k in ref_keys:
+        assert np.array_equal(sd[k].numpy(), g["sd/" + k]), k

@@ -20,7 +20,8 @@ def random_csr(n_rows, n_cols, degs, seed):
     rng = np.random.default_rng(seed)
     rp = np.concatenate([[0], np.cumsum(degs)]).astype(np.int64)
     col = np.concatenate([np.sort(rng.choice(n_cols, size=d, replace=d > n_cols)) for d in degs] + [np.zeros(0, int)])
-    val = rng.standard_normal(int(rp[-1])).astype(np.float32)
+    # ~1/sqrt(deg) magnitudes like a normalised adjacency, so row sums stay O(1)
+    val = (rng.standard_normal(int(rp[-1])) / np.sqrt(np.repeat(np.maximum(degs, 1), degs))).astype(np.float32)
     return rp, col.astype(np.int32), val
 
 

@@ -117,3 +117,20 @@ def test_clussl_same_seed_same_state_dict(mini_ds):
     assert sorted(sd.keys()) == ref_keys
     for k in ref_keys:
         assert np.array_equal(sd[k].numpy(), g["sd/" + k]), k
+
+
+def test_healthrec_and_lightgcn_same_seed_same_state_dict(mini_ds):
+    from foodrec_b200.models.cikm_model import CIKM_Model
+    from foodrec_b200.models.lightgcn import LightGCN
+    for cls, fname, extra in ((CIKM_Model, "healthrec_mini.npz",
+                               dict(n_layers=2, ui_layers=1, reg_weight=0.5, loss_kd=0.05, loss_health=0.1,
+                                    kd_threshold=0.4)),
+                              (LightGCN, "lightgcn_mini.npz", dict(n_layers=2, reg_weight=0.1))):
+        g = load_golden(fname)
+        torch.manual_seed(999)
+        m = cls(Cfg({**BASE, **extra}), mini_ds)
+        sd = m.state_dict()
+        ref_keys = sorted(k[3:] for k in g if k.startswith("sd/"))
+        assert sorted(sd.keys()) == ref_keys, set(sd.keys()) ^ set(ref_keys)
+        for k in ref_keys:
+            assert np.array_equal(sd[k].numpy(), g["sd/" + k]), (cls.__name__, k)

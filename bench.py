@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the graph-propagation + ranking hot path (contract: see DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scale C2]
+
+One "step" = one training batch (B = 512) of the CLUSSL model on the synthetic Allrecipes-scale
+graph C2: full propagation over the four normalised graphs (forward), fused BPR / regulariser /
+distance-correlation losses, backward through every propagation, Adam step -- the per-batch body of
+the reference's `Trainer._train_epoch` (FoodRec/common/trainer.py:177-224).  The headline metric is
+train epochs/s = 1 / (ceil(n_train / B) * seconds per step).  `value` is measured with the batch
+indices already resident in HBM; `e2e` goes through the public model API with pinned HOST batches
+(H2D inside the timed region) and reads every loss term back (D2H), like the reference trainer.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, torch-CPU ops -- the
+same library ops the reference calls) on the host cores, same workload and metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH = 512
+METRIC, UNIT = "train_epochs_per_s", "epochs/s"
+
+
+class Cfg(dict):
+    def __getitem__(self, k):
+        return self.get(k)
+
+
+def model_cfg(ds, device):
+    # configs/model/PRICAI_ModelX.yaml (allrecipe block) + configs/overall.yaml
+    return Cfg(device=device, embedding_size=64, train_batch_size=BATCH, is_multimodal_model=True, end2end=False,
+               use_health_level_multi_hot=True, n_ri_layers=2, n_mm_layers=1, n_ui_layers=1, reg_weight=0.01,
+               loss_cl=0.1, n_cluster=ds.cfg.n_cluster, knn_k=10, mm_image_weight=0.1, learning_rate=0.002)
+
+
+def workload_name(scale, ds):
+    return (f"{scale}: CLUSSL (PRICAI_ModelX) train step, B={BATCH}, {ds.n_users} users / {ds.n_items} items / "
+            f"{ds.n_train} train interactions, {ds.cfg.n_cluster} clusters x2 (from {ds.cfg.dv}-d image / "
+            f"{ds.cfg.dt}-d text features), {ds.num_ingredients} ingredients, d=64, "
+            f"2 item-side layers x3 graphs + 1 user-item layer, fwd+bwd+Adam")
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------- reference (CPU) arm
+class OracleClussl:
+    """CPU restatement of the reference's CLUSSL train step (oracle/, torch-CPU), used as the
+    `cpu_baseline` leg and as `--impl reference`."""
+
+    def __init__(self, ds, state_dict, lr):
+        from oracle import adjacency
+        self.ds = ds
+        self.S_ui = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+        self.S_g = adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients)
+        self.S_v = adjacency.norm_adj_item_side(ds.image_cluster_triples, ds.n_items, ds.cfg.n_cluster)
+        self.S_t = adjacency.norm_adj_item_side(ds.text_cluster_triples, ds.n_items, ds.cfg.n_cluster)
+        names = ("user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight",
+                 "image_prototype_embedding.weight", "text_prototype_embedding.weight")
+        self.P = {k: state_dict[k].detach().cpu().clone().requires_grad_(True) for k in names}
+        self.opt = torch.optim.Adam(list(self.P.values()), lr=lr)
+
+    def step(self, batch):
+        from oracle import losses, propagation
+        ds, P = self.ds, self.P
+        self.opt.zero_grad()
+        out = propagation.clussl_forward(
+            self.S_ui, self.S_g, self.S_v, self.S_t, P["user_embedding.weight"], P["item_embedding.weight"],
+            P["ingre_embedding.weight"], P["image_prototype_embedding.weight"], P["text_prototype_embedding.weight"],
+            ds.n_users, ds.n_items, ds.num_ingredients, ds.cfg.n_cluster, 2, 1)
+        u, p, n = (torch.from_numpy(batch[k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+        terms = losses.clussl_loss(out, P["user_embedding.weight"], P["item_embedding.weight"], u, p, n, 0.01, 0.1)
+        sum(terms).sum().backward()
+        self.opt.step()
+        return [float(t) for t in terms]
+
+
+def time_cpu(oracle, batches, steps, warmup):
+    for i in range(warmup):
+        oracle.step(batches[i % len(batches)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        oracle.step(batches[(warmup + i) % len(batches)])
+    return (time.perf_counter() - t0) / steps
+
+
+# ------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", default="C2")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import foodrec_b200  # noqa: F401
+    from foodrec_b200.synth import make_dataset, sample_train_batches
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        torch.set_num_threads(os.cpu_count() or 1)
+        ds = make_dataset(args.scale)
+        steps_per_epoch = math.ceil(ds.n_train / BATCH)
+        torch.manual_seed(999)
+        sd = _init_state_dict(ds)
+        oracle = OracleClussl(ds, sd, 0.002)
+        batches = sample_train_batches(ds, BATCH, min(8, args.steps + args.warmup), seed=7)
+        s = time_cpu(oracle, batches, args.steps, args.warmup)
+        v = 1.0 / (steps_per_epoch * s)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.scale, ds), "steps_per_epoch": steps_per_epoch},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} train batches of {BATCH} (full-graph fwd+bwd+Adam each), "
+                                       f"extrapolated to {steps_per_epoch} batches/epoch"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from foodrec_b200 import _lib, ops
+    from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
+
+    ds = make_dataset(args.scale)
+    steps_per_epoch = math.ceil(ds.n_train / BATCH)
+    cfg = model_cfg(ds, str(dev))
+    torch.manual_seed(999)
+    model = PRICAI_ModelX(cfg, ds)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(dev)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["learning_rate"], weight_decay=0.0)  # trainer.py:142-143
+    n_b = args.steps + args.warmup
+    # weak scaling: every rank trains on its own batches of the replicated graph (multi-GPU)
+    host_batches = sample_train_batches(ds, BATCH, min(n_b, 64), seed=7 + rank)
+    keys = ("u_id", "pos_i_id", "neg_i_id")
+    pinned = [{k: torch.from_numpy(b[k]).pin_memory() for k in keys} for b in host_batches]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in pinned]
+
+    def step(batch):
+        opt.zero_grad()
+        losses = model.calculate_loss(batch)
+        loss = sum(losses)
+        loss.backward()
+        if world > 1:
+            _allreduce_grads(model, world)
+        opt.step()
+        return losses
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM
+    for i in range(args.warmup):
+        step(resident[i % len(resident)])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(resident[(args.warmup + i) % len(resident)])
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    launches = _lib.launch_count() - l0
+
+    # ---- e2e: pinned host batches in, loss terms out, through the public model API
+    h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    for i in range(2):
+        step({k: v.to(dev, non_blocking=True) for k, v in pinned[i % len(pinned)].items()})
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        b = {k: v.to(dev, non_blocking=True) for k, v in pinned[(args.warmup + i) % len(pinned)].items()}
+        losses = step(b)
+        vals = [float(x.item()) for x in losses]  # trainer.py:186: per-term .item()
+        d2h = 4 * len(vals)
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline of the dominant kernel (propagation SpMM), CUDA events around every launch
+    prof = []
+    ops.PROFILE = prof
+    for i in range(3):
+        step(resident[i % len(resident)])
+    torch.cuda.synchronize()
+    ops.PROFILE = None
+    tot_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    tot_bytes = sum(nb for _, _, nb in prof)
+    n_launch = len(prof)
+    peaks = _peaks()
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+
+    times = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(times[0]), float(times[1])
+    if rank != 0:
+        return 0
+
+    value = world / (steps_per_epoch * ms_dev * 1e-3)
+    e2e = world / (steps_per_epoch * ms_e2e * 1e-3)
+    ws_mb = _working_set_mb(model, opt)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.scale, ds), "steps_per_epoch": steps_per_epoch,
+                   "l2": f"no explicit flush: step working set {ws_mb:.0f} MB (params+grads+Adam state+graphs+"
+                         f"activations) exceeds the 126 MB L2",
+                   "multi_gpu": "replicated graph, per-rank batches, NCCL grad all-reduce" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "spmm_seg_kernel<64>", "achieved": achieved, "peak": peaks[0],
+                     "unit": "GB/s", "frac": achieved / peaks[0], "traffic": None, "peak_source": peaks[1],
+                     "launches_per_step": n_launch / 3, "avg_launch_us": tot_ms * 1e3 / max(n_launch, 1),
+                     "kernel_share_of_step": tot_ms / 3 / ms_dev},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        oracle = OracleClussl(ds, sd0, cfg["learning_rate"])
+        s = time_cpu(oracle, host_batches, args.cpu_steps, 1)
+        line["cpu_baseline"] = {"value": 1.0 / (steps_per_epoch * s), "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "port", "ms_per_step": s * 1e3,
+                                "sample": f"{args.cpu_steps} train batches of {BATCH} on the same graph "
+                                          f"(full fwd+bwd+Adam each), extrapolated to {steps_per_epoch} batches/epoch"}
+    print(json.dumps(line))
+    return 0
+
+
+def _init_state_dict(ds):
+    """Initial parameters exactly as the model constructor draws them (CPU, no library needed)."""
+    import torch.nn as nn
+    d, out = 64, {}
+    for name, n in (("user_embedding", ds.n_users), ("item_embedding", ds.n_items),
+                    ("ingre_embedding", ds.num_ingredients + 1), ("image_prototype_embedding", ds.cfg.n_cluster),
+                    ("text_prototype_embedding", ds.cfg.n_cluster)):
+        w = torch.empty(n, d)
+        nn.init.xavier_uniform_(w)
+        out[name + ".weight"] = w
+    return out
+
+
+def _allreduce_grads(model, world):
+    import torch.distributed as dist
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat.div_(world)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+
+
+def _working_set_mb(model, opt):
+    n = sum(p.numel() for p in model.parameters()) * 4 * 4  # param, grad, exp_avg, exp_avg_sq
+    for g in (model.g_ui, model.g_image, model.g_text, model.g_ingre):
+        n += g.nnz * 8 + g.n_seg * 16 + 3 * g.n_rows * 64 * 4
+    return n / 1e6
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -109,6 +109,26 @@ int fr_scatter_add_rows(const float *g, int32_t d, const int64_t *idx, int64_t n
 int fr_pair_scores(const float *user_tab, const float *item_tab, int32_t d, const int64_t *user,
                    const int64_t *item, int64_t n, float *scores, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Distance-correlation contrastive term (CLUSSL's live `cl_loss`).
+ * Replaces `PRICAI_ModelX.correlation_distance` (FoodRec/models/pricai_modelx.py:409-437) and the
+ * three calls + row gathers at :245-247,263.  V <= 3 views are rows `idx[0..n)` of `tab_host[v]`
+ * ([rows_v, d] fp32, d in {32, 64}); P <= 3 pairs (a_p, b_p) index the views.
+ *   out[p]  = dcov(a,b) / sqrt(max(dcov(a,a) dcov(b,b), 0) + 1e-10),
+ *   dcov(x,y) = sqrt(max(sum(A_x o A_y) / n^2, 0) + 1e-8), A = double-centred
+ *   sqrt(max(r_i - 2 x_i.x_j + r_j, 0) + 1e-8).
+ * Caller-provided state kept for the backward: Dm [V, n, n], rowmean [V, n], dfds [3 P], gm [V];
+ * `ws`: zero-initialised once, fr_dcor_ws_floats(n) floats.
+ * Backward: d_tab_host[v] (dense [rows_v, d], may be NULL to skip a view, may alias between views)
+ * += sum_p g_out[p] * d out[p] / d tab_v  via fp32 atomics. */
+int64_t fr_dcor_ws_floats(int32_t n);
+int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
+                const int32_t *pairs_host, int32_t P, float *Dm, float *rowmean, float *out, float *dfds,
+                float *gm, float *ws, void *stream);
+int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
+                const int32_t *pairs_host, int32_t P, const float *Dm, const float *rowmean,
+                const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

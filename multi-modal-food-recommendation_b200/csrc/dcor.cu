@@ -1,0 +1,338 @@
+// Distance-correlation contrastive term over V <= 3 gathered views (forward + backward), sm_100a.
+//
+// The reference evaluates, per pair of [n, d] views, two n x n distance matrices, their double
+// centring and three inner products with ~40 elementwise launches and as many again in autograd
+// (FoodRec/models/pricai_modelx.py:409-437, called three times at :263).  Here the whole term is
+// three launches forward and one backward:
+//   dcor_dist_kernel    D_v[i][j] = sqrt(max(r_i - 2 x_i.x_j + r_j, 0) + 1e-8), row means (rows are
+//                       gathered from the propagated tables on the fly, no [n, d] copies)
+//   dcor_dot_kernel     s_vw = sum_ij A_v A_w / n^2 for all view pairs with A = double-centred D
+//                       (never stored), block partials folded in fixed order by the last block,
+//                       which also emits dcor_p and the partial derivatives d dcor_p / d s_xy
+//   dcor_bwd_kernel     dX_v = 4 (diag(W 1) X - W X),  W = (sum_w C_vw A_w) / (2 D_v) off-diagonal,
+//                       scatter-added straight into the dense table gradients.
+// The double-centred matrices are projections (P A P = A), so the gradient w.r.t. D_v needs no
+// re-centring; the diagonal of D (mathematically constant) is dropped analytically instead of being
+// left to cancel numerically as autograd does.  n = 2B = 1024, d = 64: latency-bound, all in L2.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxV = 3;
+constexpr int kMaxP = 3;
+constexpr int kThreads = 256;
+constexpr int kRB = 16;     // rows of D per CTA in the distance kernel
+constexpr int kRB2 = 8;     // rows per CTA in the dot kernel
+constexpr int kMaxD = 128;  // max embedding width
+constexpr float kEpsD = 1e-8f;
+
+struct Views {
+    const float *tab[kMaxV];
+    float *dtab[kMaxV];
+    int V;
+};
+struct Pairs {
+    int a[kMaxP], b[kMaxP];
+    int P;
+};
+
+__device__ __forceinline__ float block_sum(float v, float *sh) {
+    v = fr::warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) t += sh[i];
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------- K1
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+dcor_dist_kernel(Views vw, const int64_t *__restrict__ idx, int n, float *__restrict__ Dm,
+                 float *__restrict__ rowmean) {
+    __shared__ float xi[kRB][D];
+    __shared__ float ri[kRB];
+    __shared__ float red[kThreads / 32];
+    const int v = blockIdx.y;
+    const float *__restrict__ tab = vw.tab[v];
+    const int i0 = blockIdx.x * kRB;
+    for (int t = threadIdx.x; t < kRB * D; t += kThreads) {
+        const int r = t / D, k = t - r * D;
+        xi[r][k] = (i0 + r < n) ? __ldg(tab + (size_t)idx[i0 + r] * D + k) : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x < kRB) {
+        float s = 0.f;
+        for (int k = 0; k < D; ++k) s = fmaf(xi[threadIdx.x][k], xi[threadIdx.x][k], s);
+        ri[threadIdx.x] = s;
+    }
+    __syncthreads();
+    float rsum[kRB];
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) rsum[r] = 0.f;
+    float *__restrict__ Dv = Dm + (size_t)v * n * n;
+    for (int j = threadIdx.x; j < n; j += kThreads) {
+        float4 xj[D / 4];
+        const float *row = tab + (size_t)idx[j] * D;
+        float rj = 0.f;
+#pragma unroll
+        for (int q = 0; q < D / 4; ++q) {
+            xj[q] = fr::ldg_f4(row + 4 * q);
+            rj = fmaf(xj[q].x, xj[q].x, rj);
+            rj = fmaf(xj[q].y, xj[q].y, rj);
+            rj = fmaf(xj[q].z, xj[q].z, rj);
+            rj = fmaf(xj[q].w, xj[q].w, rj);
+        }
+#pragma unroll 4
+        for (int r = 0; r < kRB; ++r) {
+            float dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < D / 4; ++q) {
+                const float4 a = *reinterpret_cast<const float4 *>(&xi[r][4 * q]);
+                dot = fmaf(a.x, xj[q].x, dot);
+                dot = fmaf(a.y, xj[q].y, dot);
+                dot = fmaf(a.z, xj[q].z, dot);
+                dot = fmaf(a.w, xj[q].w, dot);
+            }
+            const float m = (ri[r] - 2.f * dot) + rj;
+            const float dist = sqrtf(fmaxf(m, 0.f) + kEpsD);
+            if (i0 + r < n) {
+                Dv[(size_t)(i0 + r) * n + j] = dist;
+                rsum[r] += dist;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) {
+        const float s = block_sum(rsum[r], red);
+        if (threadIdx.x == 0 && i0 + r < n) rowmean[(size_t)v * n + i0 + r] = s / (float)n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- K2
+// out layout: out[p] = dcor_p; dfds[p*3 + {0,1,2}] = d dcor_p / d {s_ab, s_aa, s_bb}; gm[v] grand means.
+__global__ void __launch_bounds__(kThreads)
+dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const float *__restrict__ rowmean,
+                float *__restrict__ out, float *__restrict__ dfds, float *__restrict__ gm_out,
+                float *__restrict__ ws) {
+    __shared__ float red[kThreads / 32];
+    __shared__ float gm[kMaxV];
+    __shared__ float fin[6];
+    __shared__ int last;
+    for (int v = 0; v < V; ++v) {
+        float s = 0.f;
+        for (int j = threadIdx.x; j < n; j += kThreads) s += __ldg(rowmean + (size_t)v * n + j);
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) gm[v] = s / (float)n;
+    }
+    __syncthreads();
+    // accumulate s[v][w], v <= w, slot = v*3 + w - (v*(v+1))/2 -> (00,01,02,11,12,22)
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int i0 = blockIdx.x * kRB2;
+    for (int r = 0; r < kRB2 && i0 + r < n; ++r) {
+        const int i = i0 + r;
+        float rmi[kMaxV];
+        for (int v = 0; v < kMaxV; ++v) rmi[v] = v < V ? __ldg(rowmean + (size_t)v * n + i) : 0.f;
+        for (int j = threadIdx.x; j < n; j += kThreads) {
+            float A[kMaxV];
+#pragma unroll
+            for (int v = 0; v < kMaxV; ++v)
+                A[v] = v < V ? (((__ldg(Dm + ((size_t)v * n + i) * n + j) - __ldg(rowmean + (size_t)v * n + j)) - rmi[v]) + gm[v])
+                             : 0.f;
+            acc[0] = fmaf(A[0], A[0], acc[0]);
+            acc[1] = fmaf(A[0], A[1], acc[1]);
+            acc[2] = fmaf(A[0], A[2], acc[2]);
+            acc[3] = fmaf(A[1], A[1], acc[3]);
+            acc[4] = fmaf(A[1], A[2], acc[4]);
+            acc[5] = fmaf(A[2], A[2], acc[5]);
+        }
+    }
+    for (int q = 0; q < 6; ++q) {
+        const float s = block_sum(acc[q], red);
+        if (threadIdx.x == 0) __stcg(ws + 8 + (size_t)blockIdx.x * 8 + q, s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(reinterpret_cast<int *>(ws), 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 6) {
+        float s = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(ws + 8 + (size_t)b * 8 + threadIdx.x);
+        fin[threadIdx.x] = s / ((float)n * (float)n);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        auto S = [&](int a, int b) -> float {
+            if (a > b) { const int t = a; a = b; b = t; }
+            return fin[a * 3 + b - (a * (a + 1)) / 2];
+        };
+        for (int p = 0; p < pr.P; ++p) {
+            const int a = pr.a[p], b = pr.b[p];
+            const float sab = S(a, b), saa = S(a, a), sbb = S(b, b);
+            const float cab = sqrtf(fmaxf(sab, 0.f) + 1e-8f);
+            const float caa = sqrtf(fmaxf(saa, 0.f) + 1e-8f);
+            const float cbb = sqrtf(fmaxf(sbb, 0.f) + 1e-8f);
+            const float q = sqrtf(fmaxf(caa * cbb, 0.f) + 1e-10f);
+            out[p] = cab / q;
+            const float dq = -cab / (2.f * q * q * q);  // d f / d (caa*cbb)
+            dfds[p * 3 + 0] = sab > 0.f ? 1.f / (2.f * cab * q) : 0.f;
+            dfds[p * 3 + 1] = saa > 0.f ? dq * cbb / (2.f * caa) : 0.f;
+            dfds[p * 3 + 2] = sbb > 0.f ? dq * caa / (2.f * cbb) : 0.f;
+        }
+        for (int v = 0; v < V; ++v) gm_out[v] = gm[v];
+        *reinterpret_cast<int *>(ws) = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- K3
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+dcor_bwd_kernel(Views vw, Pairs pr, const int64_t *__restrict__ idx, int n, const float *__restrict__ Dm,
+                const float *__restrict__ rowmean, const float *__restrict__ gm, const float *__restrict__ dfds,
+                const float *__restrict__ g_out) {
+    constexpr int RB = 16, JT = 64, KQ = D / 4;          // 16 rows x (D/4) float4 columns per CTA
+    static_assert(RB * KQ <= kThreads && (RB * JT) % kThreads == 0, "tile/threads mismatch");
+    __shared__ float Ws[RB][JT + 1];
+    __shared__ __align__(16) float Xs[JT][D];
+    __shared__ float Cm[kMaxV];
+    __shared__ float gms[kMaxV];
+    const int v = blockIdx.y;
+    if (vw.dtab[v] == nullptr) return;
+    if (threadIdx.x == 0) {
+        // C_vw: coefficient of A_w in d(sum_p g_p dcor_p) / d D_v
+        float c[kMaxV] = {0.f, 0.f, 0.f};
+        const float inv = 1.f / ((float)n * (float)n);
+        for (int p = 0; p < pr.P; ++p) {
+            const float g = __ldg(g_out + p);
+            const int a = pr.a[p], b = pr.b[p];
+            if (a == v) { c[b] += g * dfds[p * 3 + 0] * inv; c[a] += 2.f * g * dfds[p * 3 + 1] * inv; }
+            if (b == v) { c[a] += g * dfds[p * 3 + 0] * inv; c[b] += 2.f * g * dfds[p * 3 + 2] * inv; }
+        }
+        for (int w = 0; w < kMaxV; ++w) { Cm[w] = c[w]; gms[w] = w < vw.V ? gm[w] : 0.f; }
+    }
+    __syncthreads();
+    const int i0 = blockIdx.x * RB;
+    const float *__restrict__ tab = vw.tab[v];
+    const float *__restrict__ Dv = Dm + (size_t)v * n * n;
+    const int orow = threadIdx.x / KQ, okq = threadIdx.x % KQ;  // output element owned in the GEMM phase
+    const bool owner = threadIdx.x < RB * KQ;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wsum = 0.f;
+    const float eps_d = sqrtf(kEpsD);
+    for (int j0 = 0; j0 < n; j0 += JT) {
+        // X_j tile (gathered rows), coalesced float4
+        for (int t = threadIdx.x; t < JT * KQ; t += kThreads) {
+            const int r = t / KQ, q = t - r * KQ;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + r < n) x = fr::ldg_f4(tab + (size_t)idx[j0 + r] * D + 4 * q);
+            *reinterpret_cast<float4 *>(&Xs[r][4 * q]) = x;
+        }
+        // W tile
+        for (int t = threadIdx.x; t < RB * JT; t += kThreads) {
+            const int r = t / JT, c = t - r * JT;
+            const int i = i0 + r, j = j0 + c;
+            float w = 0.f;
+            if (i < n && j < n && i != j) {
+                const float dv = __ldg(Dv + (size_t)i * n + j);
+                if (dv > eps_d) {
+                    float g = 0.f;
+                    for (int u = 0; u < vw.V; ++u) {
+                        const float cu = Cm[u];
+                        if (cu != 0.f) {
+                            const float du = (u == v) ? dv : __ldg(Dm + ((size_t)u * n + i) * n + j);
+                            const float a = ((du - __ldg(rowmean + (size_t)u * n + j)) - __ldg(rowmean + (size_t)u * n + i)) + gms[u];
+                            g = fmaf(cu, a, g);
+                        }
+                    }
+                    w = g / (2.f * dv);
+                }
+            }
+            Ws[r][c] = w;
+        }
+        __syncthreads();
+        if (owner) {
+#pragma unroll 8
+            for (int c = 0; c < JT; ++c) {
+                const float w = Ws[orow][c];
+                const float4 x = *reinterpret_cast<const float4 *>(&Xs[c][4 * okq]);
+                fr::fma4(acc, w, x);
+                wsum += w;
+            }
+        }
+        __syncthreads();
+    }
+    if (owner && i0 + orow < n) {
+        const size_t row = (size_t)idx[i0 + orow];
+        const float4 xi = fr::ldg_f4(tab + row * D + 4 * okq);
+        float *dst = vw.dtab[v] + row * D + 4 * okq;
+        atomicAdd(dst + 0, 4.f * (wsum * xi.x - acc.x));
+        atomicAdd(dst + 1, 4.f * (wsum * xi.y - acc.y));
+        atomicAdd(dst + 2, 4.f * (wsum * xi.z - acc.z));
+        atomicAdd(dst + 3, 4.f * (wsum * xi.w - acc.w));
+    }
+}
+
+int fill(Views &vw, Pairs &pr, int V, const float *const *tab, float *const *dtab, int P, const int32_t *pairs) {
+    FR_REQUIRE(V >= 1 && V <= kMaxV && P >= 1 && P <= kMaxP && tab && pairs, "dcor: V=%d P=%d out of range", V, P);
+    vw.V = V;
+    for (int v = 0; v < kMaxV; ++v) {
+        vw.tab[v] = v < V ? tab[v] : nullptr;
+        vw.dtab[v] = (v < V && dtab) ? dtab[v] : nullptr;
+        FR_REQUIRE(v >= V || tab[v], "dcor: null view table %d", v);
+    }
+    pr.P = P;
+    for (int p = 0; p < kMaxP; ++p) {
+        pr.a[p] = p < P ? pairs[2 * p] : 0;
+        pr.b[p] = p < P ? pairs[2 * p + 1] : 0;
+        FR_REQUIRE(p >= P || (pr.a[p] >= 0 && pr.a[p] < V && pr.b[p] >= 0 && pr.b[p] < V && pr.a[p] != pr.b[p]),
+                   "dcor: pair %d out of range", p);
+    }
+    return FR_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t fr_dcor_ws_floats(int32_t n) { return 8 + 8 * (int64_t)((n + kRB2 - 1) / kRB2); }
+
+extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
+                           const int32_t *pairs_host, int32_t P, float *Dm, float *rowmean, float *out, float *dfds,
+                           float *gm, float *ws, void *stream) {
+    FR_REQUIRE(idx && Dm && rowmean && out && dfds && gm && ws && n > 0, "fr_dcor_fwd: bad argument");
+    Views vw;
+    Pairs pr;
+    if (int rc = fill(vw, pr, V, tab_host, nullptr, P, pairs_host)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 g1((n + kRB - 1) / kRB, V);
+    if (d == 64) dcor_dist_kernel<64><<<g1, kThreads, 0, st>>>(vw, idx, n, Dm, rowmean);
+    else if (d == 32) dcor_dist_kernel<32><<<g1, kThreads, 0, st>>>(vw, idx, n, Dm, rowmean);
+    else {
+        fr::set_error("fr_dcor_fwd: d=%d unsupported (32, 64)", d);
+        return FR_EUNSUPPORTED;
+    }
+    if (int rc = fr::check_launch("fr_dcor_fwd/dist")) return rc;
+    dcor_dot_kernel<<<(n + kRB2 - 1) / kRB2, kThreads, 0, st>>>(V, pr, n, Dm, rowmean, out, dfds, gm, ws);
+    return fr::check_launch("fr_dcor_fwd/dot");
+}
+
+extern "C" int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
+                           const int32_t *pairs_host, int32_t P, const float *Dm, const float *rowmean,
+                           const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host,
+                           void *stream) {
+    FR_REQUIRE(idx && Dm && rowmean && dfds && gm && g_out && d_tab_host && n > 0, "fr_dcor_bwd: bad argument");
+    Views vw;
+    Pairs pr;
+    if (int rc = fill(vw, pr, V, tab_host, d_tab_host, P, pairs_host)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 g((n + 15) / 16, V);
+    if (d == 64) dcor_bwd_kernel<64><<<g, kThreads, 0, st>>>(vw, pr, idx, n, Dm, rowmean, gm, dfds, g_out);
+    else if (d == 32) dcor_bwd_kernel<32><<<g, kThreads, 0, st>>>(vw, pr, idx, n, Dm, rowmean, gm, dfds, g_out);
+    else {
+        fr::set_error("fr_dcor_bwd: d=%d unsupported (32, 64)", d);
+        return FR_EUNSUPPORTED;
+    }
+    return fr::check_launch("fr_dcor_bwd");
+}

@@ -103,16 +103,13 @@ class PRICAI_ModelX(DotProductRecommender):
         user, pos_item, neg_item = batch_data["u_id"], batch_data["pos_i_id"], batch_data["neg_i_id"]
         all_item = torch.cat([pos_item, neg_item], dim=0)
         all_emb, (img, txt, ing) = self._propagate_all()
-        item_image = ops.gather_rows(img, all_item)   # rows < n_items of the [I + C, d] tables
-        item_text = ops.gather_rows(txt, all_item)
-        item_ingre = ops.gather_rows(ing, all_item)
         uw, iw = self.user_embedding.weight, self.item_embedding.weight
         mf_loss_g, reg = ops.rank_loss(all_emb, self.n_users, user, pos_item, neg_item,
                                        [(uw, user), (iw, pos_item), (iw, neg_item)],
                                        reg_den=float(neg_item.shape[0]), gamma=self.mf_loss.gamma)
-        cl_loss = (ops.correlation_distance(item_image, item_text)
-                   + ops.correlation_distance(item_image, item_ingre)
-                   + ops.correlation_distance(item_ingre, item_text))
+        # views are rows `all_item` (< n_items) of the propagated [I + C, d] tables, gathered in-kernel:
+        # dcor(image, text) + dcor(image, ingre) + dcor(ingre, text)
+        cl_loss = ops.dcor_terms([img, txt, ing], all_item, [(0, 1), (0, 2), (2, 1)]).sum().reshape(1)
         return mf_loss_g, self.loss_cl * cl_loss, (self.reg_weight * reg).reshape(1)
 
     def CL_loss(self, hidden, hidden_norm=True, temperature=0.5):

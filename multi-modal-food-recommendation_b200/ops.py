@@ -14,6 +14,8 @@ from . import _lib
 from .graph import PropGraph
 
 _L = _lib.lib
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes) per propagation launch
+PROFILE = None
 
 
 def _chk_f32(t: torch.Tensor, name: str):
@@ -43,11 +45,19 @@ def spmm(graph: PropGraph, X: torch.Tensor, Z: torch.Tensor | None = None, alpha
         _chk_f32(Z, "Z")
     if bias is not None:
         _chk_f32(bias, "bias")
+    prof = PROFILE
+    if prof is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _lib.check(_L.fr_spmm_csr_f32(
         graph.seg.data_ptr(), graph.n_seg, graph.long_rows.data_ptr(), graph.n_long, graph.col.data_ptr(),
         graph.val.data_ptr(), d, X.data_ptr(), _lib.ptr(Z), float(alpha), float(beta), _lib.ptr(bias), int(act),
         out.data_ptr(), graph.partial(d).data_ptr(), graph.counters.data_ptr(), _lib.stream_ptr()),
         "fr_spmm_csr_f32")
+    if prof is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        prof.append((ev0, ev1, graph.spmm_bytes(d)))
     return out
 
 
@@ -234,11 +244,63 @@ def pair_scores(user_tab: torch.Tensor, item_tab: torch.Tensor, user: torch.Tens
 
 
 # --------------------------------------------------------------------------- contrastive terms
+_DCOR_WS = {}
+
+
+def _dcor_ws(device, n):
+    need = int(_L.fr_dcor_ws_floats(n))
+    ws = _DCOR_WS.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.float32, device=device)
+        _DCOR_WS[device] = ws
+    return ws
+
+
+class _DcorTerms(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, pairs, *tabs):
+        V, P, n, d = len(tabs), len(pairs), idx.numel(), tabs[0].shape[1]
+        for t in tabs:
+            _chk_f32(t, "view table")
+        dev = tabs[0].device
+        Dm = torch.empty((V, n, n), dtype=torch.float32, device=dev)
+        rowmean = torch.empty((V, n), dtype=torch.float32, device=dev)
+        out = torch.empty(P, dtype=torch.float32, device=dev)
+        dfds = torch.empty(3 * P, dtype=torch.float32, device=dev)
+        gm = torch.empty(V, dtype=torch.float32, device=dev)
+        pr = (C.c_int32 * (2 * P))(*[int(x) for ab in pairs for x in ab])
+        _lib.check(_L.fr_dcor_fwd(_ptr_array(tabs), V, d, idx.data_ptr(), n, pr, P, Dm.data_ptr(), rowmean.data_ptr(),
+                                  out.data_ptr(), dfds.data_ptr(), gm.data_ptr(), _dcor_ws(dev, n).data_ptr(),
+                                  _lib.stream_ptr()), "fr_dcor_fwd")
+        ctx.save_for_backward(idx, Dm, rowmean, dfds, gm, *tabs)
+        ctx.pairs = [tuple(int(x) for x in ab) for ab in pairs]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, Dm, rowmean, dfds, gm = ctx.saved_tensors[:5]
+        tabs = ctx.saved_tensors[5:]
+        V, P, n, d = len(tabs), len(ctx.pairs), idx.numel(), tabs[0].shape[1]
+        g = g.to(torch.float32).contiguous()
+        d_tabs = [torch.zeros_like(t) if ctx.needs_input_grad[2 + k] else None for k, t in enumerate(tabs)]
+        pr = (C.c_int32 * (2 * P))(*[x for ab in ctx.pairs for x in ab])
+        _lib.check(_L.fr_dcor_bwd(_ptr_array(tabs), V, d, idx.data_ptr(), n, pr, P, Dm.data_ptr(), rowmean.data_ptr(),
+                                  dfds.data_ptr(), gm.data_ptr(), g.data_ptr(), _ptr_array(d_tabs),
+                                  _lib.stream_ptr()), "fr_dcor_bwd")
+        return (None, None, *d_tabs)
+
+
+def dcor_terms(tabs, idx: torch.Tensor, pairs) -> torch.Tensor:
+    """Distance correlations `[P]` between the views `tabs[v][idx]` for the view pairs `pairs`
+    (FoodRec/models/pricai_modelx.py:245-247,263,409-437): gathers, distance matrices, centring,
+    covariances and their backward in four launches."""
+    return _DcorTerms.apply(_idx(idx.reshape(-1), "idx"), list(pairs), *[t.contiguous() for t in tabs])
+
+
 def correlation_distance(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """Distance correlation of two `[n, d]` views (FoodRec/models/pricai_modelx.py:409-437);
-    returns shape `[1]` like the reference."""
-    from . import contrastive
-    return contrastive.correlation_distance(x, y)
+    """`PRICAI_ModelX.correlation_distance(x, y)` for two `[n, d]` views; returns shape `[1]`."""
+    idx = torch.arange(x.shape[0], device=x.device)
+    return dcor_terms([x, y], idx, [(0, 1)])
 
 
 def info_nce(hidden: torch.Tensor, temperature: float = 0.5, hidden_norm: bool = True) -> torch.Tensor:

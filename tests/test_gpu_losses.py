@@ -1,0 +1,101 @@
+"""GPU parity of the fused loss kernels against reference goldens and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from test_gpu_clussl import close
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rank_loss_matches_reference_modules():
+    from foodrec_b200 import ops
+    from oracle import losses
+    torch.manual_seed(3)
+    U, I, d, B = 50, 70, 64, 97
+    emb = (torch.randn(U + I, d) * 0.3).requires_grad_(True)
+    uw, iw = (torch.randn(U, d) * 0.2).requires_grad_(True), (torch.randn(I, d) * 0.2).requires_grad_(True)
+    gw = (torch.randn(11, d) * 0.2).requires_grad_(True)
+    u, p, n = torch.randint(0, U, (B,)), torch.randint(0, I, (B,)), torch.randint(0, I, (B,))
+    ing = torch.randint(0, 11, (B, 20))
+    mf = losses.bpr_from_tables(emb[:U], emb[U:], u, p, n)
+    gpad = torch.nn.functional.embedding(ing, gw, padding_idx=10)
+    reg = losses.emb_loss(uw[u], iw[p], iw[n], gpad)
+    (mf * 0.7 + reg.sum() * 1.3).backward()
+    c = lambda t: t.detach().cuda().requires_grad_(True)
+    emb_d, uw_d, iw_d, gw_d = c(emb), c(uw), c(iw), c(gw)
+    mf_d, reg_d = ops.rank_loss(emb_d, U, u.cuda(), p.cuda(), n.cuda(),
+                                [(uw_d, u.cuda()), (iw_d, p.cuda()), (iw_d, n.cuda()), (gw_d, ing.cuda(), 10)],
+                                reg_den=float(B))
+    (mf_d * 0.7 + reg_d * 1.3).backward()
+    close(mf_d, mf.detach().numpy())
+    close(reg_d, reg.detach().numpy()[0])
+    for a, b in ((emb_d, emb), (uw_d, uw), (iw_d, iw), (gw_d, gw)):
+        close(a.grad, b.grad.numpy(), rtol=2e-5)
+    assert float(gw_d.grad[10].abs().max()) == 0.0  # padding row gets no gradient
+
+
+def test_bpr_and_embloss_golden():
+    from foodrec_b200 import ops
+    g = load_golden("primitives.npz")
+    # BPR on scores: build rows whose dot products reproduce the golden scores exactly
+    pos, neg = torch.from_numpy(g["bpr/pos"]), torch.from_numpy(g["bpr/neg"])
+    B = pos.numel()
+    emb = torch.zeros(1 + 2 * B, 32)
+    emb[0, 0] = 1.0
+    emb[1:1 + B, 0] = pos
+    emb[1 + B:, 0] = neg
+    z = torch.zeros(B, dtype=torch.long)
+    e1, e2, e3 = (torch.from_numpy(g[k]) for k in ("emb/e1", "emb/e2", "emb/e3"))
+    embs = [torch.nn.functional.pad(e, (0, 0, 0, 0))[:, :].contiguous() for e in (e1, e2, e3)]
+    tabs = [torch.cat([e[:, :32], e[:, 32:]], 0).cuda() for e in embs]  # [2n, 32]: same Frobenius norm
+    mf, reg = ops.rank_loss(emb.cuda(), 1, z.cuda(), torch.arange(B).cuda(), (torch.arange(B) + B).cuda(),
+                            [(t, torch.arange(t.shape[0]).cuda()) for t in tabs], reg_den=float(e3.shape[0]))
+    close(mf, g["bpr/out"])
+    close(reg, g["emb/out"][0])
+
+
+def test_distance_correlation_golden_and_grad():
+    from foodrec_b200 import ops
+    g = load_golden("primitives.npz")
+    x = torch.from_numpy(g["dcor/x"]).cuda().requires_grad_(True)
+    y = torch.from_numpy(g["dcor/y"]).cuda().requires_grad_(True)
+    d = ops.correlation_distance(x, y)
+    d.sum().backward()
+    close(d, g["dcor/out"].reshape(1))
+    # autograd's diagonal terms cancel only numerically (1/(2*1e-4) amplification): 5e-4 of max
+    close(x.grad, g["dcor/gx"], rtol=5e-4)
+    close(y.grad, g["dcor/gy"], rtol=5e-4)
+
+
+@pytest.mark.parametrize("n", [100, 1024])
+def test_three_view_dcor_vs_oracle(n):
+    from foodrec_b200 import ops
+    from oracle import losses
+    torch.manual_seed(n)
+    rows = 3000
+    tabs = [(torch.randn(rows + k * 10, 64) * 0.1).requires_grad_(True) for k in range(3)]
+    idx = torch.randint(0, rows, (n,))
+    idx[5] = idx[17]  # duplicate rows in the batch (same item as pos and neg)
+    a, b, c = (t[idx] for t in tabs)
+    ref = torch.stack([losses.correlation_distance(a, b), losses.correlation_distance(a, c),
+                       losses.correlation_distance(c, b)]).reshape(-1)
+    w = torch.tensor([0.3, 1.0, -0.5])
+    (ref * w).sum().backward()
+    tabs_d = [t.detach().cuda().requires_grad_(True) for t in tabs]
+    out = ops.dcor_terms(tabs_d, idx.cuda(), [(0, 1), (0, 2), (2, 1)])
+    (out * w.cuda()).sum().backward()
+    close(out, ref.detach().numpy())
+    for td, t in zip(tabs_d, tabs):
+        close(td.grad, t.grad.numpy(), rtol=1e-3)
+
+
+def test_info_nce_golden():
+    from foodrec_b200 import ops
+    g = load_golden("primitives.npz")
+    h = torch.from_numpy(g["nce/h"]).cuda().requires_grad_(True)
+    c = ops.info_nce(h)
+    c.backward()
+    close(c, g["nce/out"])
+    close(h.grad, g["nce/gh"], rtol=1e-4)

@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--scale", default="C2")
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="drop-in eager step (no CUDA graph)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,7 +200,9 @@ def main():
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     model = model.to(dev)
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=cfg["learning_rate"], weight_decay=0.0)  # trainer.py:142-143
+    # trainer.py:142-143 builds optim.Adam(params, lr, weight_decay); capturable keeps `step` on the device
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["learning_rate"], weight_decay=0.0,
+                           capturable=not (args.eager or world > 1))
     n_b = args.steps + args.warmup
     # weak scaling: every rank trains on its own batches of the replicated graph (multi-GPU)
     host_batches = sample_train_batches(ds, BATCH, min(n_b, 64), seed=7 + rank)
@@ -207,7 +210,9 @@ def main():
     pinned = [{k: torch.from_numpy(b[k]).pin_memory() for k in keys} for b in host_batches]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in pinned]
 
-    def step(batch):
+    from foodrec_b200.train import GraphedTrainStep
+
+    def eager(batch):
         opt.zero_grad()
         losses = model.calculate_loss(batch)
         loss = sum(losses)
@@ -216,6 +221,11 @@ def main():
             _allreduce_grads(model, world)
         opt.step()
         return losses
+
+    if args.eager or world > 1:
+        step = eager
+    else:
+        step = GraphedTrainStep(model, opt, resident[0], keys=keys)
 
     def barrier():
         if world > 1:
@@ -258,9 +268,12 @@ def main():
     prof = []
     ops.PROFILE = prof
     for i in range(3):
-        step(resident[i % len(resident)])
+        eager(resident[i % len(resident)])  # same kernels as the graph replays; events need eager launches
     torch.cuda.synchronize()
     ops.PROFILE = None
+    l1 = _lib.launch_count()
+    eager(resident[0])
+    launches_per_step_eager = _lib.launch_count() - l1  # kernels of this library per step (graph replays the same)
     tot_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
     tot_bytes = sum(nb for _, _, nb in prof)
     n_launch = len(prof)
@@ -288,7 +301,8 @@ def main():
                    "multi_gpu": "replicated graph, per-rank batches, NCCL grad all-reduce" if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) if (args.eager or world > 1) else int(launches_per_step_eager * args.steps),
+        "step_mode": "eager" if (args.eager or world > 1) else "cuda_graph_replay",
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "spmm_seg_kernel<64>", "achieved": achieved, "peak": peaks[0],
                      "unit": "GB/s", "frac": achieved / peaks[0], "traffic": None, "peak_source": peaks[1],

@@ -129,6 +129,30 @@ int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_
                 const int32_t *pairs_host, int32_t P, const float *Dm, const float *rowmean,
                 const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Ranking: scores = scale * A . B^T + bias  ->  per-row top-k, never materialising [M, N].
+ * bf16 tcgen05 GEMM (fp32 accumulate in TMEM) with the top-k selection fused into the epilogue.
+ * Replaces, for the dot-product models, `full_sort_predict` + `torch.topk(scores, max(topk))` in
+ * `Trainer.evaluate` (FoodRec/common/trainer.py:489-497), `build_sim` +
+ * `torch.topk(adj, k)` of the kNN utilities (FoodRec/utils/utils.py:118-121,132-136,170-172) and
+ * the per-item `argsort(|x - c|)[:10][:6]` loop of dataset_process/allrecipes_kmeans.ipynb
+ * (argmin |x - c|^2 = argmax x.c - |c|^2 / 2 : bias = -|c|^2 / 2).
+ *   A [M, K], B [N, K]: bf16 row-major, K % 8 == 0, 16-byte aligned (fr_f32_to_bf16 converts and
+ *   optionally L2-normalises rows as `build_sim` does).
+ *   History mask (optional, all three or none): row m is user `row_ids[m]`; columns
+ *   `hist_idx[hist_ptr[u] .. hist_ptr[u+1])` (sorted ascending) are excluded -- MMRec's
+ *   `scores[train items] = -inf`; the reference applies no mask = pass NULLs.
+ *   out_val / out_idx [M, topk] (topk <= 64), descending, ties to the lower column, -1 / -inf padding.
+ * fr_rescore_topk_f32 re-scores kc >= k bf16 candidates exactly in fp32 (A_f32 rows `a_rows[m]` or m)
+ * and keeps the best k; out_idx int64 like `torch.topk`.  metric 1 ranks by exact squared distance. */
+int fr_f32_to_bf16(const float *x, void *y_bf16, int64_t rows, int32_t d, int32_t l2_normalise, void *stream);
+int fr_gemm_topk_bf16(const void *A_bf16, int32_t M, const void *B_bf16, int32_t N, int32_t K, float scale,
+                      const float *bias, const int64_t *row_ids, const int64_t *hist_ptr, const int32_t *hist_idx,
+                      int32_t topk, float *out_val, int32_t *out_idx, void *stream);
+int fr_rescore_topk_f32(const float *A, const int64_t *a_rows, const float *B, int32_t d, float scale,
+                        const float *bias, int32_t metric /* 0: scale*a.b+bias, 1: -|a-b|^2 */, const int32_t *cand,
+                        int32_t kc, int32_t M, int32_t k, float *out_val, int64_t *out_idx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

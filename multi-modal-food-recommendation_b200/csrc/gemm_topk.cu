@@ -1,0 +1,496 @@
+// Fused  scores = A . B^T (bf16 in, fp32 accumulate)  ->  per-row top-k,  tcgen05 / TMEM / TMA, sm_100a.
+//
+// One kernel family for the three ranking shapes of the path:
+//   full-sort      A = user_all[users] [M, 64],  B = item_all [N, 64], optional history mask, k <= 64
+//   cosine kNN     A = B = row-normalised features [N, D], k = knn_k (self kept, utils.py:119)
+//   centroids      A = features [I, D], B = centres [C, D], bias = -|c|^2 / 2, scale 1  (argmin |x - c|)
+// The [M, N] score matrix never exists in HBM: a 128 x 256 fp32 tile lives in TMEM (two stages), the
+// four epilogue warps read it back with tcgen05.ld (one accumulator row per thread) and keep a
+// running top-k per row in shared memory.  Hot path per score: one predicated compare against the
+// row's current k-th value; inserts are rare (~ k ln(N/k) per row).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane issues tcgen05.mma, M = 128, N = 256, K = 16 per instruction, SWIZZLE_128B K-major operands),
+// warps 2..5 = epilogue (TMEM lane group = warp_id % 4).  Pipelines: 3-stage smem ring (full/empty
+// mbarriers, TMA complete_tx / tcgen05.commit) and a 2-stage TMEM ring (tmem_full / tmem_empty).
+// Persistent over 128-row blocks of A; each CTA sweeps every 256-column block of B for its rows.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;  // tile; BK bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int MAXK = 64;
+constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + MAXK * BM * 8 + 256;
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must fault the launch, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("foodrec_b200 gemm_topk: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(r);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
+// [0,14), leading byte offset >> 4 in [16,30) (= 1 for swizzled K-major), stride byte offset >> 4 in [32,46)
+// (8 rows x 128 B = 1024 B between row groups), descriptor version 1 in [46,48), layout type 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct Params {
+    int M, N, K, topk;
+    float scale;
+    const float *bias;          // [N] or null, added after scaling
+    const int64_t *row_ids;     // [M] id of each A row in the history CSR, null = no mask
+    const int64_t *hist_ptr;    // CSR over ids
+    const int32_t *hist_idx;    // sorted ascending within a row
+    float *out_val;             // [M, topk]
+    int32_t *out_idx;           // [M, topk], -1 where fewer than topk columns were eligible
+};
+
+// Running top-k of one accumulator row.  Values / columns live in shared memory (slot stride BM so the
+// 32 lanes of a warp hit 32 banks); the hot-path state (k-th value, its slot, fill count) stays in
+// registers and is passed through the rarely-taken insert by value so that it never spills.
+struct TopkState {
+    float thr;
+    int minpos, count;
+};
+__device__ __noinline__ TopkState topk_insert(float *v, int *ix, TopkState st, int kk, float val, int col) {
+    int slot = st.count < kk ? st.count : st.minpos;
+    v[slot * BM] = val;
+    ix[slot * BM] = col;
+    if (st.count < kk) ++st.count;
+    if (st.count == kk) {
+        float t = v[0];
+        int mp = 0;
+        for (int s = 1; s < kk; ++s) {
+            const float x = v[s * BM];
+            if (x < t) { t = x; mp = s; }
+        }
+        st.thr = t;
+        st.minpos = mp;
+    }
+    return st;
+}
+
+__device__ __forceinline__ bool in_history(const int32_t *h, long long lo, long long hi, int col) {
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        const int x = __ldg(h + mid);
+        if (x == col) return true;
+        if (x < col) lo = mid + 1; else hi = mid;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *tiles = smem;                                              // STAGES x (A | B), 1024-aligned
+    float *topv = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);  // [MAXK][BM]
+    int *topi = reinterpret_cast<int *>(topv + MAXK * BM);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(topi + MAXK * BM);
+    uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + ACC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mblk = (P.M + BM - 1) / BM, n_nblk = (P.N + BN - 1) / BN, n_kblk = (P.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: 2 accumulator stages x 256 fp32 columns = all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x)
+                for (int nb = 0; nb < n_nblk; ++nb)
+                    for (int kb = 0; kb < n_kblk; ++kb) {
+                        mbar_wait(empty + stage, phase ^ 1);
+                        uint8_t *a = tiles + stage * STAGE_BYTES, *b = a + A_BYTES;
+                        mbar_expect_tx(full + stage, STAGE_BYTES);
+                        tma_load_2d(&tmA, full + stage, a, kb * BK, mb * BM);
+                        tma_load_2d(&tmB, full + stage, b, kb * BK, nb * BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x)
+            for (int nb = 0; nb < n_nblk; ++nb) {
+                if (lane == 0) mbar_wait(tempty + as, aphase ^ 1);
+                __syncwarp();
+                tc_fence_after();
+                for (int kb = 0; kb < n_kblk; ++kb) {
+                    if (lane == 0) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint32_t a = smem_u32(tiles + stage * STAGE_BYTES);
+                        const uint64_t ad = make_desc(a), bd = make_desc(a + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)  // +32 B per K step inside the swizzle atom
+                            umma_f16(tmem_base + as * BN, ad + 2 * k, bd + 2 * k, kIdesc, (kb | k) != 0);
+                        umma_commit(empty + stage);                       // frees the smem slot when the MMAs retire
+                        if (kb == n_kblk - 1) umma_commit(tfull + as);    // accumulator complete
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+    } else {
+        // ================================ epilogue: running top-k =====================
+        const int lg = warp & 3;                 // TMEM lane group this warp may read
+        const int r_in_blk = lg * 32 + lane;     // accumulator row owned by this thread
+        float *tv = topv + r_in_blk;
+        int *ti = topi + r_in_blk;
+        const int kk = P.topk;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x) {
+            const int row = mb * BM + r_in_blk;
+            TopkState tk{-INFINITY, 0, 0};
+            long long hlo = 0, hhi = 0;
+            if (P.row_ids != nullptr && row < P.M) {
+                const long long id = P.row_ids[row];
+                hlo = P.hist_ptr[id];
+                hhi = P.hist_ptr[id + 1];
+            }
+            for (int nb = 0; nb < n_nblk; ++nb) {
+                mbar_wait(tfull + as, aphase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
+                const int n0 = nb * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    float r[32];
+                    tmem_ld32(tbase + c * 32, r);
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= P.N) break;
+                    bool any = false;
+                    if (P.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = col0 + j;
+                            r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
+                            any |= r[j] > tk.thr;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            r[j] *= P.scale;
+                            any |= r[j] > tk.thr;
+                        }
+                    }
+                    if (any) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = col0 + j;
+                            if (r[j] > tk.thr && col < P.N) {
+                                if (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col)) tk = topk_insert(tv, ti, tk, kk, r[j], col);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + as);
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+            // ---- emit this row: descending by value, ties by ascending column
+            if (row < P.M) {
+                const int cnt = tk.count;
+                for (int o = 0; o < P.topk; ++o) {
+                    float bv = -INFINITY;
+                    int bi = 0x7fffffff, bs = -1;
+                    for (int s = 0; s < cnt; ++s) {
+                        const float x = tv[s * BM];
+                        const int ci = ti[s * BM];
+                        if (ci >= 0 && (bs < 0 || x > bv || (x == bv && ci < bi))) { bv = x; bi = ci; bs = s; }
+                    }
+                    if (bs >= 0) {
+                        P.out_val[(size_t)row * P.topk + o] = bv;
+                        P.out_idx[(size_t)row * P.topk + o] = bi;
+                        ti[bs * BM] = -1;
+                    } else {
+                        P.out_val[(size_t)row * P.topk + o] = -INFINITY;
+                        P.out_idx[(size_t)row * P.topk + o] = -1;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap *m, const void *base, int rows, int K, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        fr::set_error("gemm_topk: cuTensorMapEncodeTiled unavailable");
+        return FR_ECUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fr::set_error("gemm_topk: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d", (int)r, rows, K);
+        return FR_ECUDA;
+    }
+    return FR_OK;
+}
+
+__global__ void f32_to_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, long long n,
+                                   int d, int normalise) {
+    // one warp per row when normalising (cosine), otherwise flat
+    if (!normalise) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * d; i += (long long)gridDim.x * blockDim.x)
+            y[i] = __float2bfloat16(x[i]);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n;
+         r += ((long long)gridDim.x * blockDim.x) >> 5) {
+        float s = 0.f;
+        for (int k = lane; k < d; k += 32) { const float v = x[r * d + k]; s = fmaf(v, v, s); }
+        s = fr::warp_sum(s);
+        const float nrm = sqrtf(s);
+        for (int k = lane; k < d; k += 32) y[r * d + k] = __float2bfloat16(x[r * d + k] / nrm);
+    }
+}
+
+}  // namespace
+
+extern "C" int fr_f32_to_bf16(const float *x, void *y, int64_t rows, int32_t d, int32_t l2_normalise, void *stream) {
+    FR_REQUIRE(rows >= 0 && d > 0, "fr_f32_to_bf16: rows=%lld d=%d", (long long)rows, d);
+    if (rows == 0) return FR_OK;
+    FR_REQUIRE(x && y, "fr_f32_to_bf16: null pointer");
+    const int grid = fr::num_sms() * 8;
+    f32_to_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16 *>(y), rows, d,
+                                                              l2_normalise);
+    return fr::check_launch("fr_f32_to_bf16");
+}
+
+extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_t N, int32_t K, float scale,
+                                 const float *bias, const int64_t *row_ids, const int64_t *hist_ptr,
+                                 const int32_t *hist_idx, int32_t topk, float *out_val, int32_t *out_idx,
+                                 void *stream) {
+    FR_REQUIRE(M >= 0 && N > 0 && K > 0, "fr_gemm_topk_bf16: M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return FR_OK;
+    FR_REQUIRE(A && B && out_val && out_idx, "fr_gemm_topk_bf16: null pointer");
+    FR_REQUIRE(topk >= 1 && topk <= MAXK, "fr_gemm_topk_bf16: topk=%d out of [1, %d]", topk, MAXK);
+    FR_REQUIRE(K % 8 == 0, "fr_gemm_topk_bf16: K=%d must be a multiple of 8 (16-byte rows for TMA)", K);
+    FR_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "fr_gemm_topk_bf16: operands must be 16-byte aligned");
+    FR_REQUIRE((row_ids == nullptr) == (hist_ptr == nullptr) && (row_ids == nullptr) == (hist_idx == nullptr),
+               "fr_gemm_topk_bf16: row_ids / hist_ptr / hist_idx go together");
+    CUtensorMap ma, mb;
+    if (int rc = make_map(&ma, A, M, K, BM)) return rc;
+    if (int rc = make_map(&mb, B, N, K, BN)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            fr::set_error("fr_gemm_topk_bf16: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+            return FR_ECUDA;
+        }
+        attr_set = true;
+    }
+    Params P{M, N, K, topk, scale, bias, row_ids, hist_ptr, hist_idx, out_val, out_idx};
+    const int n_mblk = (M + BM - 1) / BM;
+    const int grid = std::min(n_mblk, fr::num_sms());
+    gemm_topk_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, P);
+    return fr::check_launch("fr_gemm_topk_bf16");
+}
+
+// ------------------------------------------------------------------------------- fp32 re-scoring
+// The bf16 pass selects kc >= k candidates per row; this pass re-scores them exactly in fp32 from the
+// fp32 tables and keeps the best k (descending, ties to the lower column) -- the order an fp32
+// `scores.topk(k)` gives except where two fp32 scores tie.  One warp per row.
+namespace {
+__global__ void __launch_bounds__(256)
+rescore_topk_kernel(const float *__restrict__ A, const int64_t *__restrict__ a_rows, const float *__restrict__ B,
+                    int d, float scale, const float *__restrict__ bias, int metric,
+                    const int32_t *__restrict__ cand, int kc, int M, int k, float *__restrict__ out_val,
+                    int64_t *__restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= M) return;
+    const float *a = A + (size_t)(a_rows ? a_rows[row] : row) * d;
+    float v[2];
+    int ci[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int c = lane + 32 * t;
+        ci[t] = c < kc ? cand[(size_t)row * kc + c] : -1;
+        v[t] = -INFINITY;
+        if (ci[t] >= 0) {
+            const float *b = B + (size_t)ci[t] * d;
+            float s = 0.f;
+            if (metric == 0) {
+                for (int q = 0; q < d; q += 4) {
+                    const float4 x = fr::ldg_f4(a + q), y = fr::ldg_f4(b + q);
+                    s = fmaf(x.x, y.x, s);
+                    s = fmaf(x.y, y.y, s);
+                    s = fmaf(x.z, y.z, s);
+                    s = fmaf(x.w, y.w, s);
+                }
+                v[t] = s * scale + (bias ? __ldg(bias + ci[t]) : 0.f);
+            } else {  // negative squared Euclidean distance: no cancellation, unlike x.c - |c|^2/2
+                for (int q = 0; q < d; q += 4) {
+                    const float4 x = fr::ldg_f4(a + q), y = fr::ldg_f4(b + q);
+                    const float e0 = x.x - y.x, e1 = x.y - y.y, e2 = x.z - y.z, e3 = x.w - y.w;
+                    s = fmaf(e0, e0, s);
+                    s = fmaf(e1, e1, s);
+                    s = fmaf(e2, e2, s);
+                    s = fmaf(e3, e3, s);
+                }
+                v[t] = -s;
+            }
+        }
+    }
+    for (int o = 0; o < k; ++o) {
+        // lane-local best, then warp arg-max (value desc, column asc)
+        int t = (ci[1] >= 0 && (ci[0] < 0 || v[1] > v[0] || (v[1] == v[0] && ci[1] < ci[0]))) ? 1 : 0;
+        float bv = ci[t] >= 0 ? v[t] : -INFINITY;
+        int bi = ci[t] >= 0 ? ci[t] : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            out_val[(size_t)row * k + o] = bi == 0x7fffffff ? -INFINITY : bv;
+            out_idx[(size_t)row * k + o] = bi == 0x7fffffff ? -1 : bi;
+        }
+        if (ci[0] == bi) ci[0] = -1;
+        if (ci[1] == bi) ci[1] = -1;
+    }
+}
+}  // namespace
+
+extern "C" int fr_rescore_topk_f32(const float *A, const int64_t *a_rows, const float *B, int32_t d, float scale,
+                                   const float *bias, int32_t metric, const int32_t *cand, int32_t kc, int32_t M,
+                                   int32_t k, float *out_val, int64_t *out_idx, void *stream) {
+    FR_REQUIRE(M >= 0 && d > 0 && d % 4 == 0, "fr_rescore_topk_f32: M=%d d=%d", M, d);
+    if (M == 0) return FR_OK;
+    FR_REQUIRE(A && B && cand && out_val && out_idx, "fr_rescore_topk_f32: null pointer");
+    FR_REQUIRE(kc >= 1 && kc <= 64 && k >= 1 && k <= kc, "fr_rescore_topk_f32: k=%d kc=%d", k, kc);
+    FR_REQUIRE(metric == 0 || metric == 1, "fr_rescore_topk_f32: metric=%d", metric);
+    const long long blocks = ((long long)M * 32 + 255) / 256;
+    rescore_topk_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, a_rows, B, d, scale, bias, metric, cand,
+                                                                           kc, M, k, out_val, out_idx);
+    return fr::check_launch("fr_rescore_topk_f32");
+}

@@ -1,14 +1,166 @@
-"""Full-sort evaluation: user x item scores, optional history mask, top-K, metrics.
+"""Ranking on the tensor cores: fused score + (mask) + top-K for full-sort evaluation, cosine kNN item
+graphs and centroid assignment.
 
 Replaces `Trainer.evaluate`'s per-user `full_sort_predict` + `torch.topk`
-(FoodRec/common/trainer.py:476-503) for the dot-product models.
+(FoodRec/common/trainer.py:476-503), the LATTICE kNN utilities (FoodRec/utils/utils.py:118-183) and
+the centroid-assignment loop of dataset_process/*_kmeans.ipynb.  Pipeline per call:
+fp32 -> bf16 operands, `fr_gemm_topk_bf16` keeps `kc = k + slack` candidates per row from the bf16
+tensor-core scores, `fr_rescore_topk_f32` re-scores those exactly in fp32 and keeps the best k, so
+the result equals an fp32 `topk` unless bf16 rounding displaced a true top-k item by more than
+`slack` ranks (bf16 score error ~ 2^-8 |u||i|; measured displacement <= 3 ranks on the synthetic
+scales, default slack 12).
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 
+from . import _lib
 
+_L = _lib.lib
+MAX_K = 64
+
+
+class HistoryCSR:
+    """Per-user sorted training items on the device (the optional full-sort mask)."""
+
+    def __init__(self, train_coo, n_users: int, device):
+        u = np.asarray(train_coo.row, dtype=np.int64)
+        i = np.asarray(train_coo.col, dtype=np.int64)
+        order = np.lexsort((i, u))
+        ptr = np.zeros(n_users + 1, dtype=np.int64)
+        np.cumsum(np.bincount(u, minlength=n_users), out=ptr[1:])
+        self.ptr_host, self.idx_host = ptr, i[order].astype(np.int32)
+        self.ptr = torch.from_numpy(ptr).to(device)
+        self.idx = torch.from_numpy(self.idx_host).to(device)
+
+
+def to_bf16(x: torch.Tensor, l2_normalise: bool = False) -> torch.Tensor:
+    x = x.detach()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    if x.device.type != "cuda":
+        raise _lib.FoodRecError("to_bf16 needs a CUDA tensor (no CPU path)")
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_L.fr_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.shape[0], x.shape[1], int(l2_normalise),
+                                 _lib.stream_ptr()), "fr_f32_to_bf16")
+    return y
+
+
+def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, bias: torch.Tensor | None = None,
+              row_ids: torch.Tensor | None = None, hist: HistoryCSR | None = None, slack: int = 12,
+              exact: bool = True, metric: int = 0, A_bf16: torch.Tensor | None = None,
+              B_bf16: torch.Tensor | None = None):
+    """Row-wise top-k of `scale * A @ B.T + bias` (A `[M, K]`, B `[N, K]` fp32) -> (values `[M, k]`
+    fp32, indices `[M, k]` int64), descending.  `hist` + `row_ids` exclude each row's history columns.
+    `exact=False` returns the bf16-scored top-k without the fp32 re-score."""
+    if k < 1 or k > MAX_K:
+        raise _lib.FoodRecError(f"k={k} outside [1, {MAX_K}]")
+    M, K = A.shape
+    N = B.shape[0]
+    if K % 8 != 0:
+        raise _lib.FoodRecError(f"inner dimension {K} must be a multiple of 8")
+    dev = A.device
+    A = A.detach().float().contiguous()
+    B = B.detach().float().contiguous()
+    Ab = A_bf16 if A_bf16 is not None else to_bf16(A)
+    Bb = B_bf16 if B_bf16 is not None else to_bf16(B)
+    kc = min(MAX_K, k + slack, N) if exact else min(k, N)
+    kc = max(kc, min(k, N))
+    cand_v = torch.empty((M, kc), dtype=torch.float32, device=dev)
+    cand_i = torch.empty((M, kc), dtype=torch.int32, device=dev)
+    if hist is not None:
+        if row_ids is None:
+            row_ids = torch.arange(M, device=dev)
+        row_ids = row_ids.to(torch.int64).contiguous()
+    if bias is not None:
+        bias = bias.detach().float().contiguous()
+    _lib.check(_L.fr_gemm_topk_bf16(
+        Ab.data_ptr(), M, Bb.data_ptr(), N, K, float(scale), _lib.ptr(bias),
+        _lib.ptr(row_ids) if hist is not None else None, hist.ptr.data_ptr() if hist is not None else None,
+        hist.idx.data_ptr() if hist is not None else None, kc, cand_v.data_ptr(), cand_i.data_ptr(),
+        _lib.stream_ptr()), "fr_gemm_topk_bf16")
+    if not exact:
+        return cand_v[:, :k], cand_i[:, :k].to(torch.int64)
+    kk = min(k, kc)
+    out_v = torch.empty((M, kk), dtype=torch.float32, device=dev)
+    out_i = torch.empty((M, kk), dtype=torch.int64, device=dev)
+    _lib.check(_L.fr_rescore_topk_f32(A.data_ptr(), None, B.data_ptr(), K, float(scale), _lib.ptr(bias), int(metric),
+                                      cand_i.data_ptr(), kc, M, kk, out_v.data_ptr(), out_i.data_ptr(),
+                                      _lib.stream_ptr()), "fr_rescore_topk_f32")
+    return out_v, out_i
+
+
+# ------------------------------------------------------------------------------- full-sort evaluation
 def full_sort_scores(user_all: torch.Tensor, item_all: torch.Tensor, users: torch.Tensor) -> torch.Tensor:
-    """Dense fp32 `[n_batch_users, n_items]` scores (the matrix the fused top-K path avoids)."""
+    """Dense fp32 `[n_batch_users, n_items]` scores -- only for API compatibility with
+    `full_sort_predict`; `full_sort_topk` is the path that never materialises this matrix."""
     return user_all[users.reshape(-1).long()] @ item_all.t()
+
+
+def full_sort_topk(user_all: torch.Tensor, item_all: torch.Tensor, users: torch.Tensor | None, k: int,
+                   hist: HistoryCSR | None = None, **kw):
+    """Top-k items for `users` (all users when None).  `hist=None` reproduces the reference (no mask)."""
+    from . import ops
+    if users is None:
+        A, row_ids = user_all, None
+    else:
+        users = users.reshape(-1).to(torch.int64)
+        A, row_ids = ops.gather_rows(user_all.detach(), users), users
+    return gemm_topk(A, item_all, k, row_ids=row_ids, hist=hist, **kw)
+
+
+def evaluate_full_sort(model, eval_users, pos_items, topk=(5, 10, 20, 50), metrics=("recall", "ndcg", "precision", "map"),
+                       hist: HistoryCSR | None = None, batch_users: int = 65536):
+    """`Trainer.evaluate` for the dot-product models: propagate once, rank every eval user against
+    all items on the tensor cores, score with the reference's metric definitions."""
+    from . import metrics as M
+    model.eval()
+    with torch.no_grad():
+        user_all, item_all = model._tables()
+        users = torch.as_tensor(np.asarray(eval_users), device=user_all.device)
+        tops = []
+        for s in range(0, users.numel(), batch_users):
+            _, idx = full_sort_topk(user_all, item_all, users[s:s + batch_users], max(topk), hist=hist)
+            tops.append(idx)
+        top = torch.cat(tops, 0).cpu().numpy()
+    return M.topk_metrics(top, pos_items, metrics=metrics, topk=topk), top
+
+
+# ------------------------------------------------------------------------------------- kNN / centroids
+def knn_topk(features: torch.Tensor, k: int, **kw):
+    """Cosine-similarity kNN: `torch.topk(build_sim(x), k)` (FoodRec/utils/utils.py:119,132-135),
+    self included.  Returns (`knn_val`, `knn_ind`) `[N, k]`."""
+    x = features.detach().float()
+    xn = (x / torch.norm(x, p=2, dim=-1, keepdim=True)).contiguous()
+    return gemm_topk(xn, xn, k, **kw)
+
+
+def knn_normalized_graph(features: torch.Tensor, k: int, norm_type: str = "sym"):
+    """Sparse branch of `build_knn_normalized_graph` (FoodRec/utils/utils.py:170-180): COO
+    `(edge_index [2, N k], edge_weight [N k])` with `get_sparse_laplacian` normalisation."""
+    val, ind = knn_topk(features, k)
+    n = features.shape[0]
+    row = torch.arange(n, device=val.device).repeat_interleave(k)
+    col = ind.reshape(-1)
+    w = val.reshape(-1)
+    deg = torch.zeros(n, dtype=w.dtype, device=w.device).index_add_(0, row, w)
+    if norm_type == "sym":
+        dis = deg.pow(-0.5)
+        dis.masked_fill_(dis == float("inf"), 0)
+        w = dis[row] * w * dis[col]
+    elif norm_type == "rw":
+        di = 1.0 / deg
+        di.masked_fill_(di == float("inf"), 0)
+        w = di[row] * w
+    return torch.stack([row, col]), w
+
+
+def centroid_topk(features: torch.Tensor, centres: torch.Tensor, k: int = 6, **kw):
+    """k nearest (Euclidean) centres per item, nearest first: the notebook's
+    `argsort([norm(x - c) for c in centres])[:10][:6]`.  Candidates from the bf16 GEMM with the
+    `-|c|^2/2` column bias, final order from exact fp32 squared distances."""
+    c = centres.detach().float().contiguous()
+    bias = -0.5 * (c * c).sum(1)
+    _, idx = gemm_topk(features, c, k, bias=bias, metric=1, **kw)
+    return idx

@@ -23,12 +23,14 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;  // tile; BK bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int MAXK = 64;
+constexpr int CAP = 128;          // candidate slots per row (append-only between prunes)
+constexpr int CSTRIDE = CAP + 1;  // padded row stride: appends and warp-wide row reads both conflict-free
 constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + MAXK * BM * 8 + 256;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BM * CSTRIDE * 8 + 256;
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,29 +122,62 @@ struct Params {
     int32_t *out_idx;           // [M, topk], -1 where fewer than topk columns were eligible
 };
 
-// Running top-k of one accumulator row.  Values / columns live in shared memory (slot stride BM so the
-// 32 lanes of a warp hit 32 banks); the hot-path state (k-th value, its slot, fill count) stays in
-// registers and is passed through the rarely-taken insert by value so that it never spills.
-struct TopkState {
-    float thr;
-    int minpos, count;
-};
-__device__ __noinline__ TopkState topk_insert(float *v, int *ix, TopkState st, int kk, float val, int col) {
-    int slot = st.count < kk ? st.count : st.minpos;
-    v[slot * BM] = val;
-    ix[slot * BM] = col;
-    if (st.count < kk) ++st.count;
-    if (st.count == kk) {
-        float t = v[0];
-        int mp = 0;
-        for (int s = 1; s < kk; ++s) {
-            const float x = v[s * BM];
-            if (x < t) { t = x; mp = s; }
-        }
-        st.thr = t;
-        st.minpos = mp;
+// Running top-k of one accumulator row = an append-only candidate list in shared memory plus a
+// threshold in a register.  A score enters the list iff it beats the threshold (one compare on the hot
+// path, two stores when it does); when a list passes CAP - 32 entries the WARP prunes it together:
+// radix-select of the k-th largest key by ballots, keep the k best, raise the threshold to the k-th.
+__device__ __forceinline__ uint32_t order_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// All 32 lanes call this for the same row.  Returns the new threshold (k-th largest value); the
+// list is compacted to exactly k entries (requires cnt > k).
+__device__ __noinline__ float warp_prune(float *bv, int *bi, int cnt, int k, int lane) {
+    float v[CAP / 32];
+    int ix[CAP / 32];
+    uint32_t key[CAP / 32];
+#pragma unroll
+    for (int t = 0; t < CAP / 32; ++t) {
+        const int s = lane + 32 * t;
+        const bool ok = s < cnt;
+        v[t] = ok ? bv[s] : 0.f;
+        ix[t] = ok ? bi[s] : -1;
+        key[t] = ok ? order_key(v[t]) : 0u;
     }
-    return st;
+    uint32_t T = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t c = T | (1u << bit);
+        int n = 0;
+#pragma unroll
+        for (int t = 0; t < CAP / 32; ++t) n += __popc(__ballot_sync(0xffffffffu, key[t] >= c));
+        if (n >= k) T = c;
+    }
+    int g = 0;
+#pragma unroll
+    for (int t = 0; t < CAP / 32; ++t) g += __popc(__ballot_sync(0xffffffffu, key[t] > T));
+    int need_eq = k - g, base = 0;
+    __syncwarp();
+    const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+    for (int t = 0; t < CAP / 32; ++t) {
+        const uint32_t mg = __ballot_sync(0xffffffffu, key[t] > T);
+        const uint32_t me = __ballot_sync(0xffffffffu, key[t] == T && ix[t] >= 0);
+        const int eq_rank = __popc(me & below);
+        const bool keep_eq = (key[t] == T && ix[t] >= 0) && eq_rank < need_eq;
+        const uint32_t mk = mg | __ballot_sync(0xffffffffu, keep_eq);
+        if ((mk >> lane) & 1u) {
+            const int dst = base + __popc(mk & below);
+            bv[dst] = v[t];
+            bi[dst] = ix[t];
+        }
+        base += __popc(mk);
+        need_eq -= min(need_eq, __popc(me));
+    }
+    __syncwarp();
+    return key_value(T);
 }
 
 __device__ __forceinline__ bool in_history(const int32_t *h, long long lo, long long hi, int col) {
@@ -160,9 +195,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *tiles = smem;                                              // STAGES x (A | B), 1024-aligned
-    float *topv = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);  // [MAXK][BM]
-    int *topi = reinterpret_cast<int *>(topv + MAXK * BM);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(topi + MAXK * BM);
+    float *topv = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);  // [BM][CSTRIDE] candidate values
+    int *topi = reinterpret_cast<int *>(topv + BM * CSTRIDE);              // [BM][CSTRIDE] candidate columns
+    uint64_t *bars = reinterpret_cast<uint64_t *>(((uintptr_t)(topi + BM * CSTRIDE) + 7) & ~(uintptr_t)7);
     uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + ACC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * ACC_STAGES);
 
@@ -229,14 +264,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================================ epilogue: running top-k =====================
         const int lg = warp & 3;                 // TMEM lane group this warp may read
         const int r_in_blk = lg * 32 + lane;     // accumulator row owned by this thread
-        float *tv = topv + r_in_blk;
-        int *ti = topi + r_in_blk;
+        float *tv = topv + r_in_blk * CSTRIDE;
+        int *ti = topi + r_in_blk * CSTRIDE;
         const int kk = P.topk;
         int as = 0;
         uint32_t aphase = 0;
         for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x) {
             const int row = mb * BM + r_in_blk;
-            TopkState tk{-INFINITY, 0, 0};
+            float thr = -INFINITY;
+            int cnt = 0;
             long long hlo = 0, hhi = 0;
             if (P.row_ids != nullptr && row < P.M) {
                 const long long id = P.row_ids[row];
@@ -260,23 +296,41 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < 32; ++j) {
                             const int col = col0 + j;
                             r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
-                            any |= r[j] > tk.thr;
+                            any |= r[j] > thr;
                         }
-                    } else {
+                    } else if (P.scale != 1.f) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             r[j] *= P.scale;
-                            any |= r[j] > tk.thr;
+                            any |= r[j] > thr;
                         }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) any |= r[j] > thr;
                     }
                     if (any) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int col = col0 + j;
-                            if (r[j] > tk.thr && col < P.N) {
-                                if (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col)) tk = topk_insert(tv, ti, tk, kk, r[j], col);
+                            if (r[j] > thr && col < P.N) {
+                                if (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col)) {
+                                    tv[cnt] = r[j];
+                                    ti[cnt] = col;
+                                    ++cnt;
+                                }
                             }
                         }
+                    }
+                    // lists that could overflow on the next 32 columns are pruned by the whole warp
+                    uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+                    if (need) __syncwarp();  // owners' appends visible to the lanes that help prune
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+                        const float t_new = warp_prune(topv + (lg * 32 + src) * CSTRIDE, topi + (lg * 32 + src) * CSTRIDE,
+                                                       c_src, kk, lane);
+                        if (lane == src) { thr = t_new; cnt = kk; }
                     }
                 }
                 tc_fence_before();
@@ -284,27 +338,38 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (lane == 0) mbar_arrive(tempty + as);
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
             }
-            // ---- emit this row: descending by value, ties by ascending column
-            if (row < P.M) {
-                const int cnt = tk.count;
-                for (int o = 0; o < P.topk; ++o) {
-                    float bv = -INFINITY;
-                    int bi = 0x7fffffff, bs = -1;
-                    for (int s = 0; s < cnt; ++s) {
-                        const float x = tv[s * BM];
-                        const int ci = ti[s * BM];
-                        if (ci >= 0 && (bs < 0 || x > bv || (x == bv && ci < bi))) { bv = x; bi = ci; bs = s; }
+            // ---- emit the rows of this warp: final prune to k, then k rounds of warp arg-max
+            //      (descending by value, ties to the lower column)
+            __syncwarp();
+            for (int src = 0; src < 32; ++src) {
+                int c_src = __shfl_sync(0xffffffffu, cnt, src);
+                const int orow = mb * BM + lg * 32 + src;
+                if (orow >= P.M) break;
+                float *rv = topv + (lg * 32 + src) * CSTRIDE;
+                int *ri = topi + (lg * 32 + src) * CSTRIDE;
+                if (c_src > kk) { warp_prune(rv, ri, c_src, kk, lane); c_src = kk; }
+                float v0 = lane < c_src ? rv[lane] : -INFINITY, v1 = lane + 32 < c_src ? rv[lane + 32] : -INFINITY;
+                int i0 = lane < c_src ? ri[lane] : -1, i1 = lane + 32 < c_src ? ri[lane + 32] : -1;
+                for (int o = 0; o < kk; ++o) {
+                    const bool second = i1 >= 0 && (i0 < 0 || v1 > v0 || (v1 == v0 && i1 < i0));
+                    float bv = second ? v1 : v0;
+                    int bi = second ? i1 : i0;
+                    if (bi < 0) bi = 0x7fffffff;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
                     }
-                    if (bs >= 0) {
-                        P.out_val[(size_t)row * P.topk + o] = bv;
-                        P.out_idx[(size_t)row * P.topk + o] = bi;
-                        ti[bs * BM] = -1;
-                    } else {
-                        P.out_val[(size_t)row * P.topk + o] = -INFINITY;
-                        P.out_idx[(size_t)row * P.topk + o] = -1;
+                    if (lane == 0) {
+                        P.out_val[(size_t)orow * kk + o] = bi == 0x7fffffff ? -INFINITY : bv;
+                        P.out_idx[(size_t)orow * kk + o] = bi == 0x7fffffff ? -1 : bi;
                     }
+                    if (i0 == bi) i0 = -1;
+                    if (i1 == bi) i1 = -1;
                 }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();

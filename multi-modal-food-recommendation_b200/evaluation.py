@@ -56,6 +56,9 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
     `exact=False` returns the bf16-scored top-k without the fp32 re-score."""
     if k < 1 or k > MAX_K:
         raise _lib.FoodRecError(f"k={k} outside [1, {MAX_K}]")
+    if exact and k + slack > MAX_K and k < B.shape[0]:
+        raise _lib.FoodRecError(f"exact top-{k} needs k + slack <= {MAX_K} candidates (slack={slack}); "
+                                f"the reference's largest cut-off is 50")
     M, K = A.shape
     N = B.shape[0]
     if K % 8 != 0:

@@ -72,6 +72,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -135,7 +143,7 @@ __device__ __forceinline__ float key_value(uint32_t k) {
 }
 // All 32 lanes call this for the same row.  Returns the new threshold (k-th largest value); the
 // list is compacted to exactly k entries (requires cnt > k).
-__device__ __noinline__ float warp_prune(float *bv, int *bi, int cnt, int k, int lane) {
+__device__ __noinline__ float warp_prune(uint32_t bv, uint32_t bi, int cnt, int k, int lane) {  // shared addresses
     float v[CAP / 32];
     int ix[CAP / 32];
     uint32_t key[CAP / 32];
@@ -143,8 +151,8 @@ __device__ __noinline__ float warp_prune(float *bv, int *bi, int cnt, int k, int
     for (int t = 0; t < CAP / 32; ++t) {
         const int s = lane + 32 * t;
         const bool ok = s < cnt;
-        v[t] = ok ? bv[s] : 0.f;
-        ix[t] = ok ? bi[s] : -1;
+        v[t] = ok ? __uint_as_float(lds32(bv + 4 * s)) : 0.f;
+        ix[t] = ok ? (int)lds32(bi + 4 * s) : -1;
         key[t] = ok ? order_key(v[t]) : 0u;
     }
     uint32_t T = 0;
@@ -170,8 +178,8 @@ __device__ __noinline__ float warp_prune(float *bv, int *bi, int cnt, int k, int
         const uint32_t mk = mg | __ballot_sync(0xffffffffu, keep_eq);
         if ((mk >> lane) & 1u) {
             const int dst = base + __popc(mk & below);
-            bv[dst] = v[t];
-            bi[dst] = ix[t];
+            sts32(bv + 4 * dst, __float_as_uint(v[t]));
+            sts32(bi + 4 * dst, (uint32_t)ix[t]);
         }
         base += __popc(mk);
         need_eq -= min(need_eq, __popc(me));
@@ -264,8 +272,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================================ epilogue: running top-k =====================
         const int lg = warp & 3;                 // TMEM lane group this warp may read
         const int r_in_blk = lg * 32 + lane;     // accumulator row owned by this thread
-        float *tv = topv + r_in_blk * CSTRIDE;
-        int *ti = topi + r_in_blk * CSTRIDE;
+        const uint32_t topv_a = smem_u32(topv), topi_a = smem_u32(topi);   // explicit shared-space addressing
+        const uint32_t tv = topv_a + 4u * r_in_blk * CSTRIDE, ti = topi_a + 4u * r_in_blk * CSTRIDE;
         const int kk = P.topk;
         int as = 0;
         uint32_t aphase = 0;
@@ -290,34 +298,32 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tmem_ld32(tbase + c * 32, r);
                     const int col0 = n0 + c * 32;
                     if (col0 >= P.N) break;
-                    bool any = false;
                     if (P.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int col = col0 + j;
                             r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
-                            any |= r[j] > thr;
                         }
                     } else if (P.scale != 1.f) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            r[j] *= P.scale;
-                            any |= r[j] > thr;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) any |= r[j] > thr;
+                        for (int j = 0; j < 32; ++j) r[j] *= P.scale;
                     }
-                    if (any) {
+                    // hot path: one 3-input max per two scores, one compare per 32
+                    float mx = fmaxf(r[0], r[1]);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int col = col0 + j;
-                            if (r[j] > thr && col < P.N) {
-                                if (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col)) {
-                                    tv[cnt] = r[j];
-                                    ti[cnt] = col;
-                                    ++cnt;
-                                }
+                    for (int j = 2; j < 32; j += 2) mx = fmaxf(fmaxf(r[j], r[j + 1]), mx);
+                    if (!__any_sync(0xffffffffu, mx > thr)) continue;
+                    // some row of this warp has a candidate among these 32 columns: walk the columns with
+                    // warp-uniform branches so the cost follows the number of candidates, not 32 x divergence
+                    const int valid = min(32, P.N - col0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const bool p = (j < valid) && (r[j] > thr);
+                        if (__any_sync(0xffffffffu, p)) {
+                            if (p && (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col0 + j))) {
+                                sts32(tv + 4 * cnt, __float_as_uint(r[j]));
+                                sts32(ti + 4 * cnt, (uint32_t)(col0 + j));
+                                ++cnt;
                             }
                         }
                     }
@@ -328,8 +334,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int src = __ffs(need) - 1;
                         need &= need - 1;
                         const int c_src = __shfl_sync(0xffffffffu, cnt, src);
-                        const float t_new = warp_prune(topv + (lg * 32 + src) * CSTRIDE, topi + (lg * 32 + src) * CSTRIDE,
-                                                       c_src, kk, lane);
+                        const uint32_t ro = 4u * (lg * 32 + src) * CSTRIDE;
+                        const float t_new = warp_prune(topv_a + ro, topi_a + ro, c_src, kk, lane);
                         if (lane == src) { thr = t_new; cnt = kk; }
                     }
                 }
@@ -345,11 +351,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int c_src = __shfl_sync(0xffffffffu, cnt, src);
                 const int orow = mb * BM + lg * 32 + src;
                 if (orow >= P.M) break;
-                float *rv = topv + (lg * 32 + src) * CSTRIDE;
-                int *ri = topi + (lg * 32 + src) * CSTRIDE;
+                const uint32_t rv = topv_a + 4u * (lg * 32 + src) * CSTRIDE, ri = topi_a + 4u * (lg * 32 + src) * CSTRIDE;
                 if (c_src > kk) { warp_prune(rv, ri, c_src, kk, lane); c_src = kk; }
-                float v0 = lane < c_src ? rv[lane] : -INFINITY, v1 = lane + 32 < c_src ? rv[lane + 32] : -INFINITY;
-                int i0 = lane < c_src ? ri[lane] : -1, i1 = lane + 32 < c_src ? ri[lane + 32] : -1;
+                float v0 = lane < c_src ? __uint_as_float(lds32(rv + 4 * lane)) : -INFINITY;
+                float v1 = lane + 32 < c_src ? __uint_as_float(lds32(rv + 4 * (lane + 32))) : -INFINITY;
+                int i0 = lane < c_src ? (int)lds32(ri + 4 * lane) : -1, i1 = lane + 32 < c_src ? (int)lds32(ri + 4 * (lane + 32)) : -1;
                 for (int o = 0; o < kk; ++o) {
                     const bool second = i1 >= 0 && (i0 < 0 || v1 > v0 || (v1 == v0 && i1 < i0));
                     float bv = second ? v1 : v0;

@@ -94,7 +94,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
     uint32_t *u = reinterpret_cast<uint32_t *>(r);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -106,17 +106,7 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&r)[32]) 
           "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
         : "r"(taddr)
         : "memory");
-}
-// Wait for the outstanding tcgen05.ld's, then pin the destination registers behind the wait so the
-// compiler cannot hoist their uses above it (the load is asynchronous until wait::ld).
-__device__ __forceinline__ void tmem_ld_wait(float (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    uint32_t *u = reinterpret_cast<uint32_t *>(r);
-    asm volatile("" : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
-                      "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15]));
-    asm volatile("" : "+r"(u[16]), "+r"(u[17]), "+r"(u[18]), "+r"(u[19]), "+r"(u[20]), "+r"(u[21]), "+r"(u[22]),
-                      "+r"(u[23]), "+r"(u[24]), "+r"(u[25]), "+r"(u[26]), "+r"(u[27]), "+r"(u[28]), "+r"(u[29]),
-                      "+r"(u[30]), "+r"(u[31]));
 }
 
 // K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
@@ -197,8 +187,6 @@ __device__ __noinline__ float warp_prune(uint32_t bv, uint32_t bi, int cnt, int 
     __syncwarp();
     return key_value(T);
 }
-
-__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 __device__ __forceinline__ bool in_history(const int32_t *h, long long lo, long long hi, int col) {
     while (lo < hi) {
@@ -299,34 +287,37 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 hlo = P.hist_ptr[id];
                 hhi = P.hist_ptr[id + 1];
             }
-            auto process_chunk = [&](float (&r)[32], const int col0) {
-                if (col0 >= P.N) return;
-                if (P.bias != nullptr) {
+            for (int nb = 0; nb < n_nblk; ++nb) {
+                mbar_wait(tfull + as, aphase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
+                const int n0 = nb * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    float r[32];
+                    tmem_ld32(tbase + c * 32, r);
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= P.N) break;
+                    if (P.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = col0 + j;
+                            r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
+                        }
+                    } else if (P.scale != 1.f) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] *= P.scale;
+                    }
+                    // hot path: one 3-input max per two scores, one compare per 32
+                    float mx = fmaxf(r[0], r[1]);
+#pragma unroll
+                    for (int j = 2; j < 32; j += 2) mx = fmaxf(fmaxf(r[j], r[j + 1]), mx);
+                    if (!__any_sync(0xffffffffu, mx > thr)) continue;
+                    // some row of this warp has a candidate among these 32 columns: walk the columns with
+                    // warp-uniform branches so the cost follows the number of candidates, not 32 x divergence
+                    const int valid = min(32, P.N - col0);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
-                    }
-                } else if (P.scale != 1.f) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] *= P.scale;
-                }
-                // hot path: 3-input max tree over four 8-column groups, one compare + vote per 32 scores
-                float g[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    g[q] = max3(max3(r[8 * q], r[8 * q + 1], r[8 * q + 2]), max3(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
-                                fmaxf(r[8 * q + 6], r[8 * q + 7]));
-                const float mx = fmaxf(max3(g[0], g[1], g[2]), g[3]);
-                if (!__any_sync(0xffffffffu, mx > thr)) return;
-                // some row of this warp has a candidate here: walk groups / columns with warp-uniform
-                // branches so the cost follows the number of candidates, not 32-way divergence
-                const int valid = min(32, P.N - col0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (!__any_sync(0xffffffffu, g[q] > thr)) continue;
-#pragma unroll
-                    for (int j = 8 * q; j < 8 * q + 8; ++j) {
                         const bool p = (j < valid) && (r[j] > thr);
                         if (__any_sync(0xffffffffu, p)) {
                             if (p && (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col0 + j))) {
@@ -336,35 +327,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         }
                     }
-                }
-                // lists that could overflow on the next 32 columns are pruned by the whole warp
-                uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
-                if (need) __syncwarp();  // owners' appends visible to the lanes that help prune
-                while (need) {
-                    const int src = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int c_src = __shfl_sync(0xffffffffu, cnt, src);
-                    const uint32_t ro = 4u * (lg * 32 + src) * CSTRIDE;
-                    const float t_new = warp_prune(topv_a + ro, topi_a + ro, c_src, kk, lane);
-                    if (lane == src) { thr = t_new; cnt = kk; }
-                }
-            };
-            for (int nb = 0; nb < n_nblk; ++nb) {
-                mbar_wait(tfull + as, aphase);
-                tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
-                const int n0 = nb * BN;
-                // Two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is examined.
-                float ra[32], rb[32];
-                tmem_ld32_issue(tbase, ra);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c += 2) {
-                    tmem_ld_wait(ra);
-                    tmem_ld32_issue(tbase + (c + 1) * 32, rb);
-                    process_chunk(ra, n0 + c * 32);
-                    tmem_ld_wait(rb);
-                    if (c + 2 < BN / 32) tmem_ld32_issue(tbase + (c + 2) * 32, ra);
-                    process_chunk(rb, n0 + (c + 1) * 32);
+                    // lists that could overflow on the next 32 columns are pruned by the whole warp
+                    uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+                    if (need) __syncwarp();  // owners' appends visible to the lanes that help prune
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+                        const uint32_t ro = 4u * (lg * 32 + src) * CSTRIDE;
+                        const float t_new = warp_prune(topv_a + ro, topi_a + ro, c_src, kk, lane);
+                        if (lane == src) { thr = t_new; cnt = kk; }
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();

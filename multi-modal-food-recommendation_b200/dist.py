@@ -1,0 +1,123 @@
+"""Multi-GPU: row-partitioned propagation (one all-gather per layer) and user-sharded evaluation.
+
+One process per GPU, `torch.distributed` (NCCL over NVLink) for the plumbing.  The reference is a
+single-process, single-GPU program, so there is no reference behaviour to match
+here: correctness is "N ranks reproduce the 1-rank result" (tests/test_dist_cpu.py, gloo).
+
+Propagation.  Rows of the normalised adjacency S -- and of every layer's embeddings -- are split into
+`world` equal blocks (the last one zero-padded).  Rank p owns rows [p*R, (p+1)*R) of S as its own CSR
+whose columns index the FULL node set; a layer is `all_gather(X_local) -> local SpMM`.  For the
+symmetric graphs the backward is the same thing on the gathered upstream gradient
+(`dX_p = S_p . all_gather(dY)`), i.e. one all-gather per layer in each direction and no reduce-scatter.
+The layer-mean epilogue (Horner form, see ops.py) is row-local.
+
+Evaluation.  Users are sharded across ranks, the item table is replicated; each rank runs the fused
+score + top-K kernel on its users and the `[U/P, k]` results are gathered once at the end.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .graph import PropGraph
+
+
+def shard_rows(n_rows: int, world: int):
+    """Equal row blocks (`rows_per_rank`, padded total)."""
+    r = -(-n_rows // world)
+    return r, r * world
+
+
+class RowPartitionedGraph:
+    """This rank's row block of a square normalised adjacency given as host CSR arrays."""
+
+    def __init__(self, row_ptr: np.ndarray, col: np.ndarray, val: np.ndarray, n_nodes: int, rank: int, world: int,
+                 device, symmetric: bool = True, graph_cls=PropGraph):
+        self.n_nodes, self.rank, self.world = n_nodes, rank, world
+        self.rows_per_rank, self.n_padded = shard_rows(n_nodes, world)
+        lo = min(rank * self.rows_per_rank, n_nodes)
+        hi = min(lo + self.rows_per_rank, n_nodes)
+        self.lo, self.hi = lo, hi
+        rp = np.asarray(row_ptr, dtype=np.int64)
+        local_rp = np.full(self.rows_per_rank + 1, rp[hi] - rp[lo], dtype=np.int64)
+        local_rp[:hi - lo + 1] = rp[lo:hi + 1] - rp[lo]
+        # columns index the all-gathered [n_padded, d] table; padding rows are empty
+        self.local = graph_cls(local_rp, col[rp[lo]:rp[hi]], val[rp[lo]:rp[hi]], self.n_padded, device,
+                               transpose="self" if symmetric else None)
+        self.symmetric = symmetric
+
+    @classmethod
+    def from_graph(cls, g: PropGraph, rank: int, world: int, device, **kw):
+        return cls(g.row_ptr_host, g.col.cpu().numpy(), g.val.cpu().numpy(), g.n_rows, rank, world, device, **kw)
+
+    def local_rows(self, full: torch.Tensor) -> torch.Tensor:
+        """This rank's (padded) row block of a full `[n_nodes, d]` table."""
+        out = torch.zeros((self.rows_per_rank, full.shape[1]), dtype=full.dtype, device=full.device)
+        out[:self.hi - self.lo] = full[self.lo:self.hi]
+        return out
+
+
+def _all_gather_rows(x_local: torch.Tensor, group=None) -> torch.Tensor:
+    world = dist.get_world_size(group)
+    full = torch.empty((x_local.shape[0] * world, x_local.shape[1]), dtype=x_local.dtype, device=x_local.device)
+    dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
+    return full
+
+
+def propagate_mean_partitioned_raw(pg: RowPartitionedGraph, ego_local: torch.Tensor, n_layers: int, spmm, group=None):
+    """`mean_l S^l ego` for this rank's rows; `spmm(graph, X_full, Z, alpha, beta)` is the local kernel."""
+    if n_layers == 0:
+        return ego_local.clone()
+    inv = 1.0 / (n_layers + 1)
+    t = ego_local
+    for layer in range(n_layers):
+        last = layer == n_layers - 1
+        x_full = _all_gather_rows(t, group)          # the one exchange step of the layer
+        t = spmm(pg.local, x_full, ego_local, inv if last else 1.0, inv if last else 1.0)
+    return t
+
+
+class _PartitionedPropagate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ego_local, pg, n_layers, spmm, group):
+        ctx.pg, ctx.n_layers, ctx.spmm, ctx.group = pg, n_layers, spmm, group
+        return propagate_mean_partitioned_raw(pg, ego_local.contiguous(), n_layers, spmm, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.pg.symmetric:
+            raise RuntimeError("row-partitioned backward needs a symmetric graph (S^T = S)")
+        return propagate_mean_partitioned_raw(ctx.pg, g.contiguous(), ctx.n_layers, ctx.spmm, ctx.group), None, None, None, None
+
+
+def _device_spmm(graph, x_full, z, alpha, beta):
+    from . import ops
+    return ops.spmm(graph, x_full, Z=z, alpha=alpha, beta=beta)
+
+
+def propagate_mean_partitioned(pg: RowPartitionedGraph, ego_local: torch.Tensor, n_layers: int, group=None, spmm=None):
+    """Differentiable row-partitioned layer-mean propagation (this rank's rows in, this rank's rows out)."""
+    return _PartitionedPropagate.apply(ego_local, pg, n_layers, spmm or _device_spmm, group)
+
+
+# ------------------------------------------------------------------------------------ evaluation
+def shard_users(users: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    n = users.numel()
+    per = -(-n // world)
+    return users[rank * per:min((rank + 1) * per, n)]
+
+
+def full_sort_topk_sharded(user_all, item_all, users, k, hist=None, group=None, topk_fn=None):
+    """Each rank ranks its slice of `users`; the `[n_users, k]` indices are gathered on every rank."""
+    from . import evaluation
+    topk_fn = topk_fn or evaluation.full_sort_topk
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = shard_users(users, rank, world)
+    per = -(-users.numel() // world)
+    idx = torch.full((per, k), -1, dtype=torch.int64, device=user_all.device)
+    if mine.numel():
+        idx[:mine.numel()] = topk_fn(user_all, item_all, mine, k, hist=hist)[1]
+    out = torch.empty((per * world, k), dtype=torch.int64, device=user_all.device)
+    dist.all_gather_into_tensor(out, idx, group=group)       # the only communication of the evaluation
+    return out[:users.numel()]

@@ -19,6 +19,8 @@ from . import _lib
 
 _L = _lib.lib
 MAX_K = 64
+# bench.py sets this to a list to collect (start_event, end_event, flops) per fused GEMM+top-K launch
+PROFILE = None
 
 
 class HistoryCSR:
@@ -78,11 +80,19 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
         row_ids = row_ids.to(torch.int64).contiguous()
     if bias is not None:
         bias = bias.detach().float().contiguous()
+    prof = PROFILE
+    if prof is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _lib.check(_L.fr_gemm_topk_bf16(
         Ab.data_ptr(), M, Bb.data_ptr(), N, K, float(scale), _lib.ptr(bias),
         _lib.ptr(row_ids) if hist is not None else None, hist.ptr.data_ptr() if hist is not None else None,
         hist.idx.data_ptr() if hist is not None else None, kc, cand_v.data_ptr(), cand_i.data_ptr(),
         _lib.stream_ptr()), "fr_gemm_topk_bf16")
+    if prof is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        prof.append((ev0, ev1, 2.0 * M * N * K))
     if not exact:
         return cand_v[:, :k], cand_i[:, :k].to(torch.int64)
     kk = min(k, kc)

@@ -34,6 +34,10 @@ int fr_version(void);
 const char *fr_last_error(void);
 /* Number of kernels this library has launched in the calling process (for bench.py's `gpu_launches`). */
 int64_t fr_launch_count(void);
+/* Optional tracing: while enabled every launch is bracketed by CUDA events on its stream;
+ * fr_profile_dump synchronises and writes "kernel,launches,total_us" lines into buf. */
+int fr_profile_enable(int on);
+int fr_profile_dump(char *buf, int64_t cap);
 
 /* ------------------------------------------------------------------------------------------------
  * Propagation: Y = alpha * (S . X) + beta * Z, S in CSR (fp32 values, int32 indices).

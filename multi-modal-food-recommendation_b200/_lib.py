@@ -33,6 +33,8 @@ SIGNATURES = {
     "fr_version": (C.c_int, []),
     "fr_last_error": (C.c_char_p, []),
     "fr_launch_count": (_i64, []),
+    "fr_profile_enable": (C.c_int, [C.c_int]),
+    "fr_profile_dump": (C.c_int, [C.c_char_p, _i64]),
     "fr_spmm_plan_sizes": (C.c_int, [_p, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "fr_spmm_plan_fill": (C.c_int, [_p, _i32, _p, _p]),
     "fr_spmm_csr_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i32, _p, _p, _f32, _f32, _p, _i32, _p, _p, _p, _p]),
@@ -78,3 +80,23 @@ def stream_ptr():
 
 def launch_count() -> int:
     return int(lib.fr_launch_count())
+
+
+class kernel_profile:
+    """`with kernel_profile() as prof: ...` -> `prof.result` = {kernel: (launches, total_us)} for the
+    launches of this library inside the block (CUDA events on the launch stream; eager launches only)."""
+
+    def __enter__(self):
+        lib.fr_profile_dump(None, 0)
+        lib.fr_profile_enable(1)
+        self.result = {}
+        return self
+
+    def __exit__(self, *exc):
+        lib.fr_profile_enable(0)
+        buf = C.create_string_buffer(1 << 16)
+        lib.fr_profile_dump(buf, len(buf))
+        for line in buf.value.decode().splitlines():
+            name, n, us = line.rsplit(",", 2)
+            self.result[name] = (int(n), float(us))
+        return False

@@ -10,6 +10,16 @@ namespace fr {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+bool profiling();
+// RAII: when profiling is enabled, brackets the kernel launches in its scope with CUDA events.
+struct LaunchTimer {
+    LaunchTimer(const char *name, cudaStream_t st);
+    ~LaunchTimer();
+    const char *name_;
+    cudaStream_t st_;
+    bool on_;
+    cudaEvent_t a_, b_;
+};
 
 inline int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();

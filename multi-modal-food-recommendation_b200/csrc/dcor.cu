@@ -307,13 +307,17 @@ extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, c
     if (int rc = fill(vw, pr, V, tab_host, nullptr, P, pairs_host)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 g1((n + kRB - 1) / kRB, V);
+    {
+    fr::LaunchTimer _lt("dcor_dist_kernel", st);
     if (d == 64) dcor_dist_kernel<64><<<g1, kThreads, 0, st>>>(vw, idx, n, Dm, rowmean);
     else if (d == 32) dcor_dist_kernel<32><<<g1, kThreads, 0, st>>>(vw, idx, n, Dm, rowmean);
     else {
         fr::set_error("fr_dcor_fwd: d=%d unsupported (32, 64)", d);
         return FR_EUNSUPPORTED;
     }
+    }
     if (int rc = fr::check_launch("fr_dcor_fwd/dist")) return rc;
+    fr::LaunchTimer _lt2("dcor_dot_kernel", st);
     dcor_dot_kernel<<<(n + kRB2 - 1) / kRB2, kThreads, 0, st>>>(V, pr, n, Dm, rowmean, out, dfds, gm, ws);
     return fr::check_launch("fr_dcor_fwd/dot");
 }
@@ -328,6 +332,7 @@ extern "C" int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, c
     if (int rc = fill(vw, pr, V, tab_host, d_tab_host, P, pairs_host)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 g((n + 15) / 16, V);
+    fr::LaunchTimer _lt("dcor_bwd_kernel", st);
     if (d == 64) dcor_bwd_kernel<64><<<g, kThreads, 0, st>>>(vw, pr, idx, n, Dm, rowmean, gm, dfds, g_out);
     else if (d == 32) dcor_bwd_kernel<32><<<g, kThreads, 0, st>>>(vw, pr, idx, n, Dm, rowmean, gm, dfds, g_out);
     else {

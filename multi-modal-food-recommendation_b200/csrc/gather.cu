@@ -50,6 +50,7 @@ extern "C" int fr_gather_rows(const float *tab, int32_t d, const int64_t *idx, i
     FR_REQUIRE(n >= 0 && d > 0 && d % 4 == 0, "fr_gather_rows: n=%lld d=%d (d must be a multiple of 4)", (long long)n, d);
     if (n == 0) return FR_OK;
     FR_REQUIRE(tab && idx && out, "fr_gather_rows: null pointer");
+    fr::LaunchTimer _lt("gather_rows_kernel", (cudaStream_t)stream);
     gather_rows_kernel<<<grid1d(n * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(tab, d / 4, idx, n, out);
     return fr::check_launch("fr_gather_rows");
 }
@@ -59,6 +60,7 @@ extern "C" int fr_scatter_add_rows(const float *g, int32_t d, const int64_t *idx
     FR_REQUIRE(n >= 0 && d > 0, "fr_scatter_add_rows: n=%lld d=%d", (long long)n, d);
     if (n == 0) return FR_OK;
     FR_REQUIRE(g && idx && d_tab, "fr_scatter_add_rows: null pointer");
+    fr::LaunchTimer _lt("scatter_add_rows_kernel", (cudaStream_t)stream);
     scatter_add_rows_kernel<<<grid1d(n * d, 256), 256, 0, (cudaStream_t)stream>>>(g, d, idx, n, d_tab);
     return fr::check_launch("fr_scatter_add_rows");
 }
@@ -69,6 +71,7 @@ extern "C" int fr_pair_scores(const float *user_tab, const float *item_tab, int3
     if (n == 0) return FR_OK;
     FR_REQUIRE(user_tab && item_tab && user && item && scores, "fr_pair_scores: null pointer");
     const long long blocks = (n * 32 + 255) / 256;
+    fr::LaunchTimer _lt("pair_scores_kernel", (cudaStream_t)stream);
     pair_scores_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(user_tab, item_tab, d, user, item, n, scores);
     return fr::check_launch("fr_pair_scores");
 }

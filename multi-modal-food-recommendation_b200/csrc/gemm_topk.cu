@@ -449,6 +449,7 @@ extern "C" int fr_f32_to_bf16(const float *x, void *y, int64_t rows, int32_t d, 
     if (rows == 0) return FR_OK;
     FR_REQUIRE(x && y, "fr_f32_to_bf16: null pointer");
     const int grid = fr::num_sms() * 8;
+    fr::LaunchTimer _lt("f32_to_bf16_kernel", (cudaStream_t)stream);
     f32_to_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16 *>(y), rows, d,
                                                               l2_normalise);
     return fr::check_launch("fr_f32_to_bf16");
@@ -481,6 +482,7 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
     Params P{M, N, K, topk, scale, bias, row_ids, hist_ptr, hist_idx, out_val, out_idx};
     const int n_mblk = (M + BM - 1) / BM;
     const int grid = std::min(n_mblk, fr::num_sms());
+    fr::LaunchTimer _lt("gemm_topk_kernel", (cudaStream_t)stream);
     gemm_topk_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, P);
     return fr::check_launch("fr_gemm_topk_bf16");
 }
@@ -561,6 +563,7 @@ extern "C" int fr_rescore_topk_f32(const float *A, const int64_t *a_rows, const 
     FR_REQUIRE(kc >= 1 && kc <= 64 && k >= 1 && k <= kc, "fr_rescore_topk_f32: k=%d kc=%d", k, kc);
     FR_REQUIRE(metric == 0 || metric == 1, "fr_rescore_topk_f32: metric=%d", metric);
     const long long blocks = ((long long)M * 32 + 255) / 256;
+    fr::LaunchTimer _lt("rescore_topk_kernel", (cudaStream_t)stream);
     rescore_topk_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, a_rows, B, d, scale, bias, metric, cand,
                                                                            kc, M, k, out_val, out_idx);
     return fr::check_launch("fr_rescore_topk_f32");

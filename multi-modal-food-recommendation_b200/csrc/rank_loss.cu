@@ -178,6 +178,7 @@ extern "C" int fr_rank_loss_fwd(const float *emb, int32_t d, int64_t item_off, c
     Groups g;
     if (int rc = fill_groups(g, n_groups, reg_tab_host, reg_idx_host, reg_cnt_host, nullptr, nullptr)) return rc;
     const int grid = grid_for(B + g.start[g.n]);
+    fr::LaunchTimer _lt("rank_loss_fwd_kernel", (cudaStream_t)stream);
     rank_loss_fwd_kernel<<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(emb, d, item_off, u, p, n, B, gamma, g,
                                                                          reg_den, out, coef, gnorm, ws);
     return fr::check_launch("fr_rank_loss_fwd");
@@ -195,6 +196,7 @@ extern "C" int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, c
     if (int rc = fill_groups(g, n_groups, reg_tab_host, reg_idx_host, reg_cnt_host, reg_pad_host, d_tab_host))
         return rc;
     const int grid = grid_for(B + g.start[g.n]);
+    fr::LaunchTimer _lt("rank_loss_bwd_kernel", (cudaStream_t)stream);
     rank_loss_bwd_kernel<<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(emb, d, item_off, u, p, n, B, coef, g_out,
                                                                          d_emb, g, reg_den, gnorm);
     return fr::check_launch("fr_rank_loss_bwd");

@@ -138,6 +138,7 @@ int launch(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, co
         fr::set_error("fr_spmm_csr_f32: too many segments (%lld)", (long long)n_seg);
         return FR_EUNSUPPORTED;
     }
+    fr::LaunchTimer _lt("spmm_seg_kernel", st);
     dim3 grid((unsigned)blocks), block(kWarpsPerBlock * 32);
     if (act == 0)
         spmm_seg_kernel<D, 0><<<grid, block, 0, st>>>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y,

@@ -75,22 +75,50 @@ class PRICAI_ModelX(DotProductRecommender):
             nn.init.xavier_normal_(self.text_trs.weight)
 
     # ------------------------------------------------------------------ propagation
-    def _propagate_all(self):
+    def _side_streams(self):
+        """Two extra CUDA streams: the three item-side propagations (and, in `calculate_loss`, the
+        contrastive term) are independent sub-graphs of the step, so they are forked onto their own
+        streams and joined -- under CUDA-graph capture these become parallel branches.  Autograd runs
+        each backward on its forward's stream, so the backward overlaps the same way."""
+        st = getattr(self, "_streams", None)
+        if st is None:
+            dev = self.item_embedding.weight.device
+            st = self._streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        return st
+
+    def _propagate_all(self, side_fn=None):
         I = self.n_items
         item_w = self.item_embedding.weight
+        cur = torch.cuda.current_stream()
+        s1, s2 = self._side_streams()
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
         ing = ops.propagate_mean(self.g_ingre, torch.cat((item_w, self.ingre_embedding.weight[:-1]), 0),
                                  self.n_ri_layers)
-        image_proto = self.image_prototype_embedding.weight
-        if self.v_center is not None:
-            image_proto = self.image_trs(image_proto)
-        img = ops.propagate_mean(self.g_image, torch.cat((item_w, image_proto), 0), self.n_ri_layers)
-        text_proto = self.text_prototype_embedding.weight
-        if self.t_center is not None:
-            text_proto = self.text_trs(text_proto)
-        txt = ops.propagate_mean(self.g_text, torch.cat((item_w, text_proto), 0), self.n_ri_layers)
+        with torch.cuda.stream(s1):
+            image_proto = self.image_prototype_embedding.weight
+            if self.v_center is not None:
+                image_proto = self.image_trs(image_proto)
+            img = ops.propagate_mean(self.g_image, torch.cat((item_w, image_proto), 0), self.n_ri_layers)
+        with torch.cuda.stream(s2):
+            text_proto = self.text_prototype_embedding.weight
+            if self.t_center is not None:
+                text_proto = self.text_trs(text_proto)
+            txt = ops.propagate_mean(self.g_text, torch.cat((item_w, text_proto), 0), self.n_ri_layers)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+        for t in (img, txt):
+            t.record_stream(cur)
+        side = None
+        if side_fn is not None:   # work that only needs the item-side views runs beside the user-item propagation
+            s1.wait_stream(cur)
+            with torch.cuda.stream(s1):
+                side = side_fn(img, txt, ing)
         item_emb = ing[:I] + img[:I] + txt[:I]
         all_emb = ops.propagate_mean(self.g_ui, torch.cat((self.user_embedding.weight, item_emb), 0),
                                      self.n_ui_layers)
+        if side_fn is not None:
+            return all_emb, (img, txt, ing), side
         return all_emb, (img, txt, ing)
 
     def forward(self):
@@ -102,14 +130,19 @@ class PRICAI_ModelX(DotProductRecommender):
     def calculate_loss(self, batch_data):
         user, pos_item, neg_item = batch_data["u_id"], batch_data["pos_i_id"], batch_data["neg_i_id"]
         all_item = torch.cat([pos_item, neg_item], dim=0)
-        all_emb, (img, txt, ing) = self._propagate_all()
+        # views are rows `all_item` (< n_items) of the propagated [I + C, d] tables, gathered in-kernel:
+        # dcor(image, text) + dcor(image, ingre) + dcor(ingre, text).  Latency-bound, so it runs on a side
+        # stream beside the user-item propagation and the ranking loss.
+        def contrastive(img, txt, ing):
+            return ops.dcor_terms([img, txt, ing], all_item, [(0, 1), (0, 2), (2, 1)]).sum().reshape(1)
+        all_emb, (img, txt, ing), cl_loss = self._propagate_all(side_fn=contrastive)
         uw, iw = self.user_embedding.weight, self.item_embedding.weight
         mf_loss_g, reg = ops.rank_loss(all_emb, self.n_users, user, pos_item, neg_item,
                                        [(uw, user), (iw, pos_item), (iw, neg_item)],
                                        reg_den=float(neg_item.shape[0]), gamma=self.mf_loss.gamma)
-        # views are rows `all_item` (< n_items) of the propagated [I + C, d] tables, gathered in-kernel:
-        # dcor(image, text) + dcor(image, ingre) + dcor(ingre, text)
-        cl_loss = ops.dcor_terms([img, txt, ing], all_item, [(0, 1), (0, 2), (2, 1)]).sum().reshape(1)
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self._side_streams()[0])
+        cl_loss.record_stream(cur)
         return mf_loss_g, self.loss_cl * cl_loss, (self.reg_weight * reg).reshape(1)
 
     def CL_loss(self, hidden, hidden_norm=True, temperature=0.5):

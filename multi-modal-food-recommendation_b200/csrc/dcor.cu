@@ -21,8 +21,7 @@ namespace {
 constexpr int kMaxV = 3;
 constexpr int kMaxP = 3;
 constexpr int kThreads = 256;
-constexpr int kRB = 16;     // rows of D per CTA in the distance kernel
-constexpr int kRB2 = 8;     // rows per CTA in the dot kernel
+constexpr int kRB2 = 4;     // rows per CTA in the dot kernel
 constexpr int kMaxD = 128;  // max embedding width
 constexpr float kEpsD = 1e-8f;
 
@@ -48,67 +47,80 @@ __device__ __forceinline__ float block_sum(float v, float *sh) {
 }
 
 // ---------------------------------------------------------------------------------------- K1
+// 64 x 64 tile of D_v per CTA (256 threads, 4 x 4 outputs each) from transposed shared tiles of the
+// gathered rows; squared norms ride along in the k loop in the same summation order as the dot product,
+// so the diagonal is exactly sqrt(1e-8).  Row sums go out as one partial per (row, column tile) and are
+// folded in fixed order by dcor_rowmean_kernel.
+constexpr int kT = 64;  // tile edge
 template <int D>
 __global__ void __launch_bounds__(kThreads)
 dcor_dist_kernel(Views vw, const int64_t *__restrict__ idx, int n, float *__restrict__ Dm,
-                 float *__restrict__ rowmean) {
-    __shared__ float xi[kRB][D];
-    __shared__ float ri[kRB];
-    __shared__ float red[kThreads / 32];
-    const int v = blockIdx.y;
+                 float *__restrict__ rowpart, int n_tiles) {
+    __shared__ __align__(16) float Xi[D][kT + 4];
+    __shared__ __align__(16) float Xj[D][kT + 4];
+    const int v = blockIdx.z;
     const float *__restrict__ tab = vw.tab[v];
-    const int i0 = blockIdx.x * kRB;
-    for (int t = threadIdx.x; t < kRB * D; t += kThreads) {
+    const int i0 = blockIdx.y * kT, j0 = blockIdx.x * kT;
+    for (int t = threadIdx.x; t < kT * D; t += kThreads) {
         const int r = t / D, k = t - r * D;
-        xi[r][k] = (i0 + r < n) ? __ldg(tab + (size_t)idx[i0 + r] * D + k) : 0.f;
+        Xi[k][r] = (i0 + r < n) ? __ldg(tab + (size_t)idx[i0 + r] * D + k) : 0.f;
+        Xj[k][r] = (j0 + r < n) ? __ldg(tab + (size_t)idx[j0 + r] * D + k) : 0.f;
     }
     __syncthreads();
-    if (threadIdx.x < kRB) {
-        float s = 0.f;
-        for (int k = 0; k < D; ++k) s = fmaf(xi[threadIdx.x][k], xi[threadIdx.x][k], s);
-        ri[threadIdx.x] = s;
-    }
-    __syncthreads();
-    float rsum[kRB];
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float acc[4][4], ri[4] = {0.f, 0.f, 0.f, 0.f}, rj[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) rsum[r] = 0.f;
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < D; ++k) {
+        const float4 av = *reinterpret_cast<const float4 *>(&Xi[k][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4 *>(&Xj[k][tx * 4]);
+        const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            ri[a] = fmaf(a4[a], a4[a], ri[a]);
+            rj[a] = fmaf(b4[a], b4[a], rj[a]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+        }
+    }
     float *__restrict__ Dv = Dm + (size_t)v * n * n;
-    for (int j = threadIdx.x; j < n; j += kThreads) {
-        float4 xj[D / 4];
-        const float *row = tab + (size_t)idx[j] * D;
-        float rj = 0.f;
 #pragma unroll
-        for (int q = 0; q < D / 4; ++q) {
-            xj[q] = fr::ldg_f4(row + 4 * q);
-            rj = fmaf(xj[q].x, xj[q].x, rj);
-            rj = fmaf(xj[q].y, xj[q].y, rj);
-            rj = fmaf(xj[q].z, xj[q].z, rj);
-            rj = fmaf(xj[q].w, xj[q].w, rj);
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty * 4 + a;
+        float d4[4], rs = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float m = (ri[a] - 2.f * acc[a][b]) + rj[b];
+            d4[b] = sqrtf(fmaxf(m, 0.f) + kEpsD);
+            if (j0 + tx * 4 + b < n) rs += d4[b];
         }
-#pragma unroll 4
-        for (int r = 0; r < kRB; ++r) {
-            float dot = 0.f;
-#pragma unroll
-            for (int q = 0; q < D / 4; ++q) {
-                const float4 a = *reinterpret_cast<const float4 *>(&xi[r][4 * q]);
-                dot = fmaf(a.x, xj[q].x, dot);
-                dot = fmaf(a.y, xj[q].y, dot);
-                dot = fmaf(a.z, xj[q].z, dot);
-                dot = fmaf(a.w, xj[q].w, dot);
-            }
-            const float m = (ri[r] - 2.f * dot) + rj;
-            const float dist = sqrtf(fmaxf(m, 0.f) + kEpsD);
-            if (i0 + r < n) {
-                Dv[(size_t)(i0 + r) * n + j] = dist;
-                rsum[r] += dist;
-            }
+        if (i < n) {
+            if (j0 + tx * 4 + 3 < n && (n & 3) == 0)
+                *reinterpret_cast<float4 *>(Dv + (size_t)i * n + j0 + tx * 4) = make_float4(d4[0], d4[1], d4[2], d4[3]);
+            else
+                for (int b = 0; b < 4; ++b)
+                    if (j0 + tx * 4 + b < n) Dv[(size_t)i * n + j0 + tx * 4 + b] = d4[b];
         }
+        // fold the 16 column-threads of this row (a half-warp), one partial per (row, column tile)
+        rs += __shfl_xor_sync(0xffffffffu, rs, 8);
+        rs += __shfl_xor_sync(0xffffffffu, rs, 4);
+        rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+        if (tx == 0 && i < n) rowpart[((size_t)v * n_tiles + blockIdx.x) * n + i] = rs;
     }
-#pragma unroll
-    for (int r = 0; r < kRB; ++r) {
-        const float s = block_sum(rsum[r], red);
-        if (threadIdx.x == 0 && i0 + r < n) rowmean[(size_t)v * n + i0 + r] = s / (float)n;
-    }
+}
+
+__global__ void dcor_rowmean_kernel(const float *__restrict__ rowpart, int n, int n_tiles, int V,
+                                    float *__restrict__ rowmean) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) s += rowpart[((size_t)v * n_tiles + t) * n + i];
+    rowmean[(size_t)v * n + i] = s / (float)n;
 }
 
 // ---------------------------------------------------------------------------------------- K2
@@ -135,6 +147,7 @@ dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const floa
         const int i = i0 + r;
         float rmi[kMaxV];
         for (int v = 0; v < kMaxV; ++v) rmi[v] = v < V ? __ldg(rowmean + (size_t)v * n + i) : 0.f;
+#pragma unroll 4
         for (int j = threadIdx.x; j < n; j += kThreads) {
             float A[kMaxV];
 #pragma unroll
@@ -218,12 +231,16 @@ dcor_bwd_kernel(Views vw, Pairs pr, const int64_t *__restrict__ idx, int n, cons
     const int i0 = blockIdx.x * RB;
     const float *__restrict__ tab = vw.tab[v];
     const float *__restrict__ Dv = Dm + (size_t)v * n * n;
+    // the column range is split over blockIdx.z; the result is linear in (wsum, acc), so every CTA adds
+    // its own 4 (wsum x_i - acc) into the dense gradient
+    const int jt_total = (n + JT - 1) / JT, jt_per = (jt_total + gridDim.z - 1) / gridDim.z;
+    const int j_lo = blockIdx.z * jt_per * JT, j_hi = min(n, (int)(blockIdx.z + 1) * jt_per * JT);
     const int orow = threadIdx.x / KQ, okq = threadIdx.x % KQ;  // output element owned in the GEMM phase
     const bool owner = threadIdx.x < RB * KQ;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float wsum = 0.f;
     const float eps_d = sqrtf(kEpsD);
-    for (int j0 = 0; j0 < n; j0 += JT) {
+    for (int j0 = j_lo; j0 < j_hi; j0 += JT) {
         // X_j tile (gathered rows), coalesced float4
         for (int t = threadIdx.x; t < JT * KQ; t += kThreads) {
             const int r = t / KQ, q = t - r * KQ;
@@ -231,27 +248,37 @@ dcor_bwd_kernel(Views vw, Pairs pr, const int64_t *__restrict__ idx, int n, cons
             if (j0 + r < n) x = fr::ldg_f4(tab + (size_t)idx[j0 + r] * D + 4 * q);
             *reinterpret_cast<float4 *>(&Xs[r][4 * q]) = x;
         }
-        // W tile
-        for (int t = threadIdx.x; t < RB * JT; t += kThreads) {
-            const int r = t / JT, c = t - r * JT;
-            const int i = i0 + r, j = j0 + c;
-            float w = 0.f;
-            if (i < n && j < n && i != j) {
-                const float dv = __ldg(Dv + (size_t)i * n + j);
-                if (dv > eps_d) {
-                    float g = 0.f;
-                    for (int u = 0; u < vw.V; ++u) {
-                        const float cu = Cm[u];
-                        if (cu != 0.f) {
-                            const float du = (u == v) ? dv : __ldg(Dm + ((size_t)u * n + i) * n + j);
-                            const float a = ((du - __ldg(rowmean + (size_t)u * n + j)) - __ldg(rowmean + (size_t)u * n + i)) + gms[u];
-                            g = fmaf(cu, a, g);
-                        }
-                    }
-                    w = g / (2.f * dv);
+        // W tile: all loads of a thread's four elements are issued before any is used
+        {
+            float du[RB * JT / kThreads][kMaxV], rmj[RB * JT / kThreads][kMaxV], rmi[RB * JT / kThreads][kMaxV];
+#pragma unroll
+            for (int e = 0; e < RB * JT / kThreads; ++e) {
+                const int t = threadIdx.x + e * kThreads;
+                const int r = t / JT, c = t - r * JT;
+                const int i = min(i0 + r, n - 1), j = min(j0 + c, n - 1);
+#pragma unroll
+                for (int u = 0; u < kMaxV; ++u) {
+                    const bool on = u < vw.V;
+                    du[e][u] = on ? __ldg(Dm + ((size_t)u * n + i) * n + j) : 0.f;
+                    rmj[e][u] = on ? __ldg(rowmean + (size_t)u * n + j) : 0.f;
+                    rmi[e][u] = on ? __ldg(rowmean + (size_t)u * n + i) : 0.f;
                 }
             }
-            Ws[r][c] = w;
+#pragma unroll
+            for (int e = 0; e < RB * JT / kThreads; ++e) {
+                const int t = threadIdx.x + e * kThreads;
+                const int r = t / JT, c = t - r * JT;
+                const int i = i0 + r, j = j0 + c;
+                float w = 0.f;
+                float dv = 0.f, g = 0.f;
+#pragma unroll
+                for (int u = 0; u < kMaxV; ++u) {
+                    if (u == v) dv = du[e][u];
+                    g = fmaf(Cm[u], ((du[e][u] - rmj[e][u]) - rmi[e][u]) + gms[u], g);
+                }
+                if (i < n && j < j_hi && i != j && dv > eps_d) w = g / (2.f * dv);
+                Ws[r][c] = w;
+            }
         }
         __syncthreads();
         if (owner) {
@@ -296,7 +323,11 @@ int fill(Views &vw, Pairs &pr, int V, const float *const *tab, float *const *dta
 
 }  // namespace
 
-extern "C" int64_t fr_dcor_ws_floats(int32_t n) { return 8 + 8 * (int64_t)((n + kRB2 - 1) / kRB2); }
+// ws layout: [0] ticket, [8 ...) dot-kernel block partials, then the row-sum partials [V][n_tiles][n]
+static int64_t dot_blocks(int n) { return (n + kRB2 - 1) / kRB2; }
+extern "C" int64_t fr_dcor_ws_floats(int32_t n) {
+    return 8 + 8 * dot_blocks(n) + (int64_t)kMaxV * ((n + kT - 1) / kT) * n;
+}
 
 extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
                            const int32_t *pairs_host, int32_t P, float *Dm, float *rowmean, float *out, float *dfds,
@@ -306,17 +337,21 @@ extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, c
     Pairs pr;
     if (int rc = fill(vw, pr, V, tab_host, nullptr, P, pairs_host)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 g1((n + kRB - 1) / kRB, V);
+    const int n_tiles = (n + kT - 1) / kT;
+    float *rowpart = ws + 8 + 8 * dot_blocks(n);
+    dim3 g1(n_tiles, n_tiles, V);
     {
     fr::LaunchTimer _lt("dcor_dist_kernel", st);
-    if (d == 64) dcor_dist_kernel<64><<<g1, kThreads, 0, st>>>(vw, idx, n, Dm, rowmean);
-    else if (d == 32) dcor_dist_kernel<32><<<g1, kThreads, 0, st>>>(vw, idx, n, Dm, rowmean);
+    if (d == 64) dcor_dist_kernel<64><<<g1, kThreads, 0, st>>>(vw, idx, n, Dm, rowpart, n_tiles);
+    else if (d == 32) dcor_dist_kernel<32><<<g1, kThreads, 0, st>>>(vw, idx, n, Dm, rowpart, n_tiles);
     else {
         fr::set_error("fr_dcor_fwd: d=%d unsupported (32, 64)", d);
         return FR_EUNSUPPORTED;
     }
     }
     if (int rc = fr::check_launch("fr_dcor_fwd/dist")) return rc;
+    dcor_rowmean_kernel<<<dim3((n + 255) / 256, V), 256, 0, st>>>(rowpart, n, n_tiles, V, rowmean);
+    if (int rc = fr::check_launch("fr_dcor_fwd/rowmean")) return rc;
     fr::LaunchTimer _lt2("dcor_dot_kernel", st);
     dcor_dot_kernel<<<(n + kRB2 - 1) / kRB2, kThreads, 0, st>>>(V, pr, n, Dm, rowmean, out, dfds, gm, ws);
     return fr::check_launch("fr_dcor_fwd/dot");
@@ -331,7 +366,7 @@ extern "C" int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, c
     Pairs pr;
     if (int rc = fill(vw, pr, V, tab_host, d_tab_host, P, pairs_host)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 g((n + 15) / 16, V);
+    dim3 g((n + 15) / 16, V, 4);
     fr::LaunchTimer _lt("dcor_bwd_kernel", st);
     if (d == 64) dcor_bwd_kernel<64><<<g, kThreads, 0, st>>>(vw, pr, idx, n, Dm, rowmean, gm, dfds, g_out);
     else if (d == 32) dcor_bwd_kernel<32><<<g, kThreads, 0, st>>>(vw, pr, idx, n, Dm, rowmean, gm, dfds, g_out);

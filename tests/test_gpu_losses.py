@@ -107,7 +107,7 @@ def test_three_view_dcor_vs_oracle(n):
     close(out, refs[torch.float32][0], rtol=1e-4)
     for td, g64, g32 in zip(tabs_d, refs[torch.float64][1], refs[torch.float32][1]):
         close(td.grad, g64, rtol=1e-4)
-        close(td.grad, g32, rtol=3e-3)
+        close(td.grad, g32, rtol=1e-2)  # the fp32 autograd reference is itself ~5e-3 noisy at n=1024 (see above)
 
 
 def test_info_nce_golden():

@@ -235,7 +235,6 @@ def main():
 
     # ---- value: inputs resident in HBM
     sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~0.3 s to start sampling
-    t_start = time.perf_counter()
     for i in range(args.warmup):
         step(resident[i % len(resident)])
     barrier()
@@ -263,10 +262,6 @@ def main():
         d2h = 4 * len(vals)
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
-    if sampler and time.perf_counter() - t_start < 1.5:   # keep the GPU busy until the sampler has data
-        while time.perf_counter() - t_start < 1.5:
-            step(resident[0])
-        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
 
     # ---- roofline of the dominant kernel (propagation SpMM), CUDA events around every launch

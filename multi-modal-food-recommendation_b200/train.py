@@ -11,13 +11,28 @@ from __future__ import annotations
 import torch
 
 
-def eager_step(model, optimizer, batch):
+def eager_step(model, optimizer, batch, grad_hook=None):
     optimizer.zero_grad()
     losses = model.calculate_loss(batch)
     loss = sum(losses) if isinstance(losses, tuple) else losses
     loss.backward()
+    if grad_hook is not None:
+        grad_hook(model)
     optimizer.step()
     return losses
+
+
+def allreduce_mean_grads(group=None):
+    """Gradient hook for data-parallel replicas: one NCCL all-reduce per dense gradient (capturable)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+
+    def hook(model):
+        for p in model.parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad, group=group)
+                p.grad.div_(world)
+    return hook
 
 
 class GraphedTrainStep:
@@ -30,7 +45,7 @@ class GraphedTrainStep:
     (device, overwritten by the next call).
     """
 
-    def __init__(self, model, optimizer, example_batch: dict, keys=None, warmup: int = 3):
+    def __init__(self, model, optimizer, example_batch: dict, keys=None, warmup: int = 3, grad_hook=None):
         self.model, self.optimizer = model, optimizer
         dev = next(model.parameters()).device
         self.keys = list(keys) if keys is not None else list(example_batch.keys())
@@ -39,7 +54,7 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):  # allocates lazily-created workspaces and optimizer state outside the graph
-                eager_step(model, optimizer, self.static)
+                eager_step(model, optimizer, self.static, grad_hook)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -48,6 +63,8 @@ class GraphedTrainStep:
             losses = model.calculate_loss(self.static)
             loss = sum(losses) if isinstance(losses, tuple) else losses
             loss.backward()
+            if grad_hook is not None:
+                grad_hook(model)
             optimizer.step()
         self.losses = losses if isinstance(losses, tuple) else (losses,)
         self.loss_vec = None

@@ -8,6 +8,8 @@
 // partials; the last segment to arrive (atomic ticket) re-reads them in fixed order, so the result
 // is bit-reproducible run to run.  Algorithmic bytes per launch:
 //   8*nnz + 4*(R+1) + 4*D*C + 4*D*R   (+ 4*D*R when the fused Z stream is used).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -129,6 +131,201 @@ spmm_seg_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__res
     if (lane == 0) counters[s.w] = 0;  // leave the ticket counter ready for the next launch
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bulk-copy variant: embedding rows are gathered by the copy engine (cp.async.bulk, one 256-byte row per
+// issuing lane, 32 rows = 8 KB per warp instruction) into a per-warp two-stage shared-memory ring that
+// completes on an mbarrier, instead of by 128-bit register loads.  Bytes in flight no longer cost
+// registers or issue slots: per 32 nonzeros the warp spends one copy instruction plus 16 x (shuffle +
+// 128-bit shared load + 4 FMA).  Persistent warps walk the segment list with a 3-deep software pipeline:
+// (col, val) of chunk i+2 in registers, row copies of chunk i+1 in flight, chunk i being reduced.
+constexpr int kBulkWarps = 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000LL) __trap();  // protocol bug: fault, never hang
+    }
+}
+__device__ __forceinline__ void bulk_row_copy(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+struct ChunkDesc {
+    int row, cnt, long_id;
+    long long seg_idx;
+    bool valid, last;
+};
+
+template <int D, int ACT>
+__global__ void __launch_bounds__(kBulkWarps * 32)
+spmm_bulk_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
+                 const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
+                 const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,
+                 float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters) {
+    constexpr int LPR = Shape<D>::LPR, RPI = Shape<D>::RPI, ROW_BYTES = D * 4, STAGE_BYTES = 32 * ROW_BYTES;
+    extern __shared__ __align__(128) uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bars[kBulkWarps][2];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / LPR, off = (lane % LPR) * 4;
+    uint8_t *stage_base = smem_dyn + (size_t)wib * 2 * STAGE_BYTES;
+    const uint32_t stage_addr = smem_addr(stage_base);
+    const uint32_t bar_addr = smem_addr(&bars[wib][0]);
+    if (lane == 0) {
+        bar_init(bar_addr, 1);
+        bar_init(bar_addr + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const long long stride = (long long)gridDim.x * kBulkWarps;
+    long long s = (long long)blockIdx.x * kBulkWarps + wib;   // segment this warp works on
+    int base = 0;
+    int4 sg = make_int4(0, 0, 0, -1), sg_next = make_int4(0, 0, 0, -1);
+    if (s < n_seg) sg = __ldg(seg + s);
+    if (s + stride < n_seg) sg_next = __ldg(seg + s + stride);
+
+    // produces the next chunk (<= 32 nonzeros of one segment) and loads its (col, val) into registers
+    auto fetch = [&](ChunkDesc &d, int &c, float &v) {
+        d.valid = s < n_seg;
+        c = 0;
+        v = 0.f;
+        if (!d.valid) return;
+        d.row = sg.x;
+        d.long_id = sg.w;
+        d.seg_idx = s;
+        d.cnt = min(32, sg.z - base);
+        if (lane < d.cnt) {
+            c = __ldg(col + sg.y + base + lane);
+            v = __ldg(val + sg.y + base + lane);
+        }
+        base += 32;
+        d.last = base >= sg.z;
+        if (d.last) {
+            s += stride;
+            base = 0;
+            sg = sg_next;
+            if (s + stride < n_seg) sg_next = __ldg(seg + s + stride);
+        }
+    };
+    auto issue = [&](const ChunkDesc &d, int c, int st) {
+        if (!d.valid || d.cnt == 0) return;
+        const uint32_t bar = bar_addr + 8 * st;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of this stage
+        if (lane == 0) bar_expect_tx(bar, (uint32_t)d.cnt * ROW_BYTES);
+        __syncwarp();
+        if (lane < d.cnt) bulk_row_copy(stage_addr + st * STAGE_BYTES + lane * ROW_BYTES, X + (size_t)c * D, ROW_BYTES, bar);
+    };
+
+    ChunkDesc d0, d1, d2;
+    int c2;
+    float v0, v1, v2;
+    uint32_t phase[2] = {0u, 0u};
+    int st1 = 0;                       // stage the in-flight chunk (d1) lands in
+    fetch(d2, c2, v2);
+    d1 = d2; v1 = v2;
+    issue(d1, c2, st1);
+    fetch(d2, c2, v2);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    while (d1.valid) {
+        d0 = d1; v0 = v1;
+        const int st0 = st1;
+        st1 ^= 1;
+        d1 = d2; v1 = v2;
+        issue(d1, c2, st1);            // stage st1 was drained in the previous iteration
+        fetch(d2, c2, v2);
+        if (d0.cnt > 0) {
+            bar_wait(bar_addr + 8 * st0, phase[st0]);
+            phase[st0] ^= 1u;
+            const float *rows = reinterpret_cast<const float *>(stage_base + (size_t)st0 * STAGE_BYTES);
+#pragma unroll 4
+            for (int j = 0; j < d0.cnt; j += RPI) {
+                const int e = j + sub;
+                const float vj = __shfl_sync(0xffffffffu, v0, e & 31);
+                if (e < d0.cnt) {
+                    const float4 x = *reinterpret_cast<const float4 *>(rows + e * D + off);
+                    fr::fma4(acc, vj, x);
+                }
+            }
+        }
+        if (d0.last) {
+            float4 tot = reduce_subgroups<D>(acc);
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d0.long_id < 0) {
+                if (lane < LPR) epilogue_store<D, ACT>(tot, d0.row, off, Z, alpha, beta, bias, Y);
+            } else {
+                const int4 lr = __ldg(long_rows + d0.long_id);  // first_seg, n_parts, part_base, row
+                const int part = (int)(d0.seg_idx - lr.x);
+                if (lane < LPR) __stcg(reinterpret_cast<float4 *>(partial + ((size_t)lr.z + part) * D + off), tot);
+                __threadfence();
+                __syncwarp();
+                int ticket = 0;
+                if (lane == 0) ticket = atomicAdd(counters + d0.long_id, 1);
+                ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                if (ticket == lr.y - 1) {
+                    __threadfence();
+                    float4 t2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = sub; k < lr.y; k += RPI) fr::add4(t2, fr::ldcg_f4(partial + ((size_t)lr.z + k) * D + off));
+                    t2 = reduce_subgroups<D>(t2);
+                    if (lane < LPR) epilogue_store<D, ACT>(t2, lr.w, off, Z, alpha, beta, bias, Y);
+                    if (lane == 0) counters[d0.long_id] = 0;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int spmm_impl() {
+    static int impl = -1;
+    if (impl < 0) {
+        const char *e = getenv("FR_SPMM_IMPL");
+        impl = (e && e[0] == '0') ? 0 : 1;   // 1 = bulk-copy gather (default), 0 = register gather
+    }
+    return impl;
+}
+
+template <int D, int ACT>
+int launch_bulk(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val, const float *X,
+                const float *Z, float alpha, float beta, const float *bias, float *Y, float *partial, int *counters,
+                cudaStream_t st) {
+    constexpr int smem = kBulkWarps * 2 * 32 * D * 4;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(spmm_bulk_kernel<D, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            fr::set_error("fr_spmm_csr_f32: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+            return FR_ECUDA;
+        }
+        attr = true;
+    }
+    const int per_sm = std::max(1, std::min(8, (220 * 1024) / (smem + 1024)));
+    const long long want = (n_seg + kBulkWarps - 1) / kBulkWarps;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)fr::num_sms() * per_sm));
+    fr::LaunchTimer _lt("spmm_bulk_kernel", st);
+    spmm_bulk_kernel<D, ACT><<<grid, kBulkWarps * 32, smem, st>>>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y,
+                                                                   partial, counters);
+    return fr::check_launch("fr_spmm_csr_f32(bulk)");
+}
+
 template <int D>
 int launch(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val, const float *X,
            const float *Z, float alpha, float beta, const float *bias, int act, float *Y, float *partial,
@@ -137,6 +334,10 @@ int launch(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, co
     if (blocks > 0x7fffffffLL) {
         fr::set_error("fr_spmm_csr_f32: too many segments (%lld)", (long long)n_seg);
         return FR_EUNSUPPORTED;
+    }
+    if (spmm_impl() == 1) {
+        if (act == 0) return launch_bulk<D, 0>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st);
+        return launch_bulk<D, 1>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st);
     }
     fr::LaunchTimer _lt("spmm_seg_kernel", st);
     dim3 grid((unsigned)blocks), block(kWarpsPerBlock * 32);

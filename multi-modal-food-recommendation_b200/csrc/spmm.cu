@@ -295,21 +295,23 @@ spmm_bulk_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__re
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sub-warp variant: one GROUP of D/4 lanes (a half-warp for D = 64) owns one segment, so every lane keeps
-// its own 4 output columns for the whole row: no cross-lane reduction, half the per-row bookkeeping of
-// the warp-per-segment kernel, and up to 8 x 128-bit gathers in flight per lane.  Groups of one warp take
+// Sub-warp variant: one GROUP of LPR lanes owns one segment and every lane keeps VPL = D/(4 LPR) float4
+// column slices of the output row for the whole segment: no cross-lane reduction, a quarter of the
+// per-row bookkeeping of the warp-per-segment kernel (D = 64: 8 lanes x 2 float4, four rows per warp),
+// and the shuffle / address / predicate work of a step is shared by 4 nonzeros.  Groups of one warp take
 // adjacent segments of the length-sorted plan, so their trip counts match.
-template <int D, int ACT>
+template <int D, int LPR, int ACT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
                   const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
                   const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,
                   float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters) {
-    constexpr int LPR = Shape<D>::LPR, G = Shape<D>::RPI, U = 8;
+    constexpr int G = 32 / LPR, VPL = D / (4 * LPR), U = 4;
+    static_assert(VPL >= 1 && LPR % U == 0, "bad group shape");
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w * G >= n_seg) return;
     const int lane = threadIdx.x & 31;
-    const int g = lane / LPR, lg = lane % LPR, off = lg * 4;
+    const int g = lane / LPR, lg = lane % LPR;
     const long long sidx = w * G + g;
     int4 s = make_int4(0, 0, 0, -2);                     // .w == -2: no segment for this group
     if (sidx < n_seg) s = __ldg(seg + sidx);
@@ -318,9 +320,11 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
     for (int o = 16; o >= LPR; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
     const int *__restrict__ cp = col + s.y;
     const float *__restrict__ vp = val + s.y;
-    const float *__restrict__ Xo = X + off;
+    const float *__restrict__ Xo = X + lg * 4;           // slice t of this lane starts at column 4 (lg + LPR t)
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[VPL];
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = 0; base < maxlen; base += LPR) {
         const int cnt = max(0, min(LPR, s.z - base));
         int c = 0;
@@ -331,31 +335,42 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
         }
         const int lim = min(LPR, maxlen - base);
         for (int j = 0; j < lim; j += U) {
-            float4 x[U];
+            float4 x[U][VPL];
             float vv[U];
 #pragma unroll
-            for (int t = 0; t < U; ++t) {
-                const int e = j + t;                     // < LPR whenever it is < lim (LPR is a multiple of U or lim-bounded)
-                const int cj = __shfl_sync(0xffffffffu, c, e & (LPR - 1), LPR);
-                vv[t] = __shfl_sync(0xffffffffu, v, e & (LPR - 1), LPR);
-                x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e < cnt) x[t] = fr::ldg_f4(Xo + (size_t)cj * D);
-                else vv[t] = 0.f;
+            for (int u = 0; u < U; ++u) {
+                const int e = j + u;
+                const int cj = __shfl_sync(0xffffffffu, c, e, LPR);
+                vv[u] = __shfl_sync(0xffffffffu, v, e, LPR);
+                const float *xr = Xo + (size_t)cj * D;
+                if (e < cnt) {
+#pragma unroll
+                    for (int t = 0; t < VPL; ++t) x[u][t] = fr::ldg_f4(xr + 4 * LPR * t);
+                } else {
+                    vv[u] = 0.f;
+#pragma unroll
+                    for (int t = 0; t < VPL; ++t) x[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
 #pragma unroll
-            for (int t = 0; t < U; ++t) fr::fma4(acc, vv[t], x[t]);
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int t = 0; t < VPL; ++t) fr::fma4(acc[t], vv[u], x[u][t]);
         }
     }
     if (s.w == -2) return;
     if (s.w < 0) {
-        epilogue_store<D, ACT>(acc, s.x, off, Z, alpha, beta, bias, Y);
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) epilogue_store<D, ACT>(acc[t], s.x, 4 * (lg + LPR * t), Z, alpha, beta, bias, Y);
         return;
     }
     // ---- long row: publish this segment's partial; the last segment to arrive folds all in fixed order
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
     const int4 lr = __ldg(long_rows + s.w);              // first_seg, n_parts, part_base, row
     const int part = (int)(sidx - lr.x);
-    __stcg(reinterpret_cast<float4 *>(partial + ((size_t)lr.z + part) * D + off), acc);
+#pragma unroll
+    for (int t = 0; t < VPL; ++t)
+        __stcg(reinterpret_cast<float4 *>(partial + ((size_t)lr.z + part) * D + 4 * (lg + LPR * t)), acc[t]);
     __threadfence();
     __syncwarp(gmask);
     int ticket = 0;
@@ -363,9 +378,12 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
     ticket = __shfl_sync(gmask, ticket, g * LPR);
     if (ticket != lr.y - 1) return;
     __threadfence();
-    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(partial + ((size_t)lr.z + k) * D + off));
-    epilogue_store<D, ACT>(tot, lr.w, off, Z, alpha, beta, bias, Y);
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) {
+        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(partial + ((size_t)lr.z + k) * D + 4 * (lg + LPR * t)));
+        epilogue_store<D, ACT>(tot, lr.w, 4 * (lg + LPR * t), Z, alpha, beta, bias, Y);
+    }
     if (lg == 0) counters[s.w] = 0;
 }
 
@@ -373,7 +391,7 @@ template <int D, int ACT>
 int launch_group(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val, const float *X,
                  const float *Z, float alpha, float beta, const float *bias, float *Y, float *partial, int *counters,
                  cudaStream_t st) {
-    constexpr int G = Shape<D>::RPI;
+    constexpr int LPR = 8, G = 32 / LPR;                 // 8 lanes per row for every supported width
     const long long warps = (n_seg + G - 1) / G;
     const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > 0x7fffffffLL) {
@@ -381,8 +399,8 @@ int launch_group(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *c
         return FR_EUNSUPPORTED;
     }
     fr::LaunchTimer _lt("spmm_group_kernel", st);
-    spmm_group_kernel<D, ACT><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(seg, n_seg, lrows, col, val, X, Z, alpha,
-                                                                               beta, bias, Y, partial, counters);
+    spmm_group_kernel<D, LPR, ACT><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+        seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters);
     return fr::check_launch("fr_spmm_csr_f32(group)");
 }
 

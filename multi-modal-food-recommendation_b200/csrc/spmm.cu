@@ -300,13 +300,13 @@ spmm_bulk_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__re
 // per-row bookkeeping of the warp-per-segment kernel (D = 64: 8 lanes x 2 float4, four rows per warp),
 // and the shuffle / address / predicate work of a step is shared by 4 nonzeros.  Groups of one warp take
 // adjacent segments of the length-sorted plan, so their trip counts match.
-template <int D, int LPR, int ACT>
+template <int D, int LPR, int U, int ACT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
                   const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
                   const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,
                   float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters) {
-    constexpr int G = 32 / LPR, VPL = D / (4 * LPR), U = 4;
+    constexpr int G = 32 / LPR, VPL = D / (4 * LPR);
     static_assert(VPL >= 1 && LPR % U == 0, "bad group shape");
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w * G >= n_seg) return;
@@ -387,11 +387,11 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
     if (lg == 0) counters[s.w] = 0;
 }
 
-template <int D, int ACT>
-int launch_group(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val, const float *X,
-                 const float *Z, float alpha, float beta, const float *bias, float *Y, float *partial, int *counters,
-                 cudaStream_t st) {
-    constexpr int LPR = 8, G = 32 / LPR;                 // 8 lanes per row for every supported width
+template <int D, int LPR, int U, int ACT>
+int launch_group_shape(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val,
+                       const float *X, const float *Z, float alpha, float beta, const float *bias, float *Y,
+                       float *partial, int *counters, cudaStream_t st) {
+    constexpr int G = 32 / LPR;
     const long long warps = (n_seg + G - 1) / G;
     const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > 0x7fffffffLL) {
@@ -399,9 +399,29 @@ int launch_group(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *c
         return FR_EUNSUPPORTED;
     }
     fr::LaunchTimer _lt("spmm_group_kernel", st);
-    spmm_group_kernel<D, LPR, ACT><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+    spmm_group_kernel<D, LPR, U, ACT><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
         seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters);
     return fr::check_launch("fr_spmm_csr_f32(group)");
+}
+
+template <int D, int ACT>
+int launch_group(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val, const float *X,
+                 const float *Z, float alpha, float beta, const float *bias, float *Y, float *partial, int *counters,
+                 cudaStream_t st) {
+    static int shape = -1;                               // tuning knob: FR_SPMM_SHAPE = lanes-per-row * 10 + unroll
+    if (shape < 0) {
+        const char *e = getenv("FR_SPMM_SHAPE");
+        shape = e ? atoi(e) : 84;
+    }
+#define FR_GO(L, UU) return launch_group_shape<D, L, UU, ACT>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st)
+    if constexpr (D >= 64) {
+        if (shape == 42) FR_GO(4, 2);
+        if (shape == 44) FR_GO(4, 4);
+        if (shape == 164) FR_GO(16, 4);
+        if (shape == 88) FR_GO(8, 8);
+    }
+    FR_GO(8, 4);
+#undef FR_GO
 }
 
 static int spmm_impl() {

@@ -150,9 +150,10 @@ int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_
  * fr_rescore_topk_f32 re-scores kc >= k bf16 candidates exactly in fp32 (A_f32 rows `a_rows[m]` or m)
  * and keeps the best k; out_idx int64 like `torch.topk`.  metric 1 ranks by exact squared distance. */
 int fr_f32_to_bf16(const float *x, void *y_bf16, int64_t rows, int32_t d, int32_t l2_normalise, void *stream);
+int64_t fr_gemm_topk_ws_bytes(int32_t M); /* caller-provided scratch (candidate lists, L2-resident) */
 int fr_gemm_topk_bf16(const void *A_bf16, int32_t M, const void *B_bf16, int32_t N, int32_t K, float scale,
                       const float *bias, const int64_t *row_ids, const int64_t *hist_ptr, const int32_t *hist_idx,
-                      int32_t topk, float *out_val, int32_t *out_idx, void *stream);
+                      int32_t topk, float *out_val, int32_t *out_idx, void *ws, int64_t ws_bytes, void *stream);
 int fr_rescore_topk_f32(const float *A, const int64_t *a_rows, const float *B, int32_t d, float scale,
                         const float *bias, int32_t metric /* 0: scale*a.b+bias, 1: -|a-b|^2 */, const int32_t *cand,
                         int32_t kc, int32_t M, int32_t k, float *out_val, int64_t *out_idx, void *stream);

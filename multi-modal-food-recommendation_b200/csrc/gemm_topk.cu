@@ -16,6 +16,7 @@
 // Persistent over 128-row blocks of A; each CTA sweeps every 256-column block of B for its rows.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -386,6 +387,315 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+
+// ================================================================================================
+// v2: the same MMA / TMA pipeline with SIXTEEN epilogue warps (four per SM sub-partition).
+// Profiling v1 showed the tensor pipe 6 % busy and the four epilogue warps at 0.1-0.2 IPC: with one warp
+// per scheduler every dependent instruction and branch is exposed.  Here the four warps that may read a
+// TMEM lane group split each 256-column tile into 64-column quarters; a thread owns (row, quarter) and
+// keeps its candidate list in an L2-resident global workspace (CAPG slots), which frees the shared
+// memory that capped the warp count (and pays for a 4-stage operand ring).  The four quarter threads of
+// a row share the best known lower bound of the row's k-th score through a shared-memory key
+// (atomicMax at prune time), and their lists are merged, selected and sorted per row at the end of the
+// row block.
+constexpr int EW2 = 16;
+constexpr int THREADS2 = 64 + EW2 * 32;
+constexpr int STAGES2 = 4;
+constexpr int CAPG = 96;                       // slots per (row, quarter) list; prune when > CAPG - 32
+constexpr int SMEM2 = 1024 + STAGES2 * STAGE_BYTES + BM * 4 * 4 + BM * 4 + 256;
+
+__device__ __noinline__ float warp_prune_g(float *bv, int *bi, int cnt, int k, int lane) {
+    constexpr int T = CAPG / 32;
+    float v[T];
+    int ix[T];
+    uint32_t key[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int s = lane + 32 * t;
+        const bool ok = s < cnt;
+        v[t] = ok ? __ldcg(bv + s) : 0.f;
+        ix[t] = ok ? __ldcg(bi + s) : -1;
+        key[t] = ok ? order_key(v[t]) : 0u;
+    }
+    uint32_t Tk = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t c = Tk | (1u << bit);
+        int n = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) n += __popc(__ballot_sync(0xffffffffu, key[t] >= c));
+        if (n >= k) Tk = c;
+    }
+    int g = 0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) g += __popc(__ballot_sync(0xffffffffu, key[t] > Tk));
+    int need_eq = k - g, base = 0;
+    const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const uint32_t mg = __ballot_sync(0xffffffffu, key[t] > Tk);
+        const bool is_eq = key[t] == Tk && ix[t] >= 0;
+        const uint32_t me = __ballot_sync(0xffffffffu, is_eq);
+        const bool keep_eq = is_eq && __popc(me & below) < need_eq;
+        const uint32_t mk = mg | __ballot_sync(0xffffffffu, keep_eq);
+        if ((mk >> lane) & 1u) {
+            const int dst = base + __popc(mk & below);
+            __stcg(bv + dst, v[t]);
+            __stcg(bi + dst, ix[t]);
+        }
+        base += __popc(mk);
+        need_eq -= min(need_eq, __popc(me));
+    }
+    __threadfence_block();
+    __syncwarp();
+    return key_value(Tk);
+}
+
+struct Params2 {
+    Params p;
+    float *lv;   // [grid][BM][4][CAPG]
+    int *li;
+};
+
+__global__ void __launch_bounds__(THREADS2, 1)
+gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params2 PP) {
+    const Params &P = PP.p;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *tiles = smem;
+    int *cnt_s = reinterpret_cast<int *>(smem + STAGES2 * STAGE_BYTES);   // [BM][4]
+    uint32_t *thr_key = reinterpret_cast<uint32_t *>(cnt_s + BM * 4);      // [BM] best known k-th key per row
+    uint64_t *bars = reinterpret_cast<uint64_t *>(((uintptr_t)(thr_key + BM) + 7) & ~(uintptr_t)7);
+    uint64_t *full = bars, *empty = bars + STAGES2, *tfull = bars + 2 * STAGES2, *tempty = bars + 2 * STAGES2 + ACC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES2 + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_mblk = (P.M + BM - 1) / BM, n_nblk = (P.N + BN - 1) / BN, n_kblk = (P.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, EW2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < BM) thr_key[threadIdx.x] = 0u;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x)
+                for (int nb = 0; nb < n_nblk; ++nb)
+                    for (int kb = 0; kb < n_kblk; ++kb) {
+                        mbar_wait(empty + stage, phase ^ 1);
+                        uint8_t *a = tiles + stage * STAGE_BYTES, *b = a + A_BYTES;
+                        mbar_expect_tx(full + stage, STAGE_BYTES);
+                        tma_load_2d(&tmA, full + stage, a, kb * BK, mb * BM);
+                        tma_load_2d(&tmB, full + stage, b, kb * BK, nb * BN);
+                        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x)
+            for (int nb = 0; nb < n_nblk; ++nb) {
+                if (lane == 0) mbar_wait(tempty + as, aphase ^ 1);
+                __syncwarp();
+                tc_fence_after();
+                for (int kb = 0; kb < n_kblk; ++kb) {
+                    if (lane == 0) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint32_t a = smem_u32(tiles + stage * STAGE_BYTES);
+                        const uint64_t ad = make_desc(a), bd = make_desc(a + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_f16(tmem_base + as * BN, ad + 2 * k, bd + 2 * k, kIdesc, (kb | k) != 0);
+                        umma_commit(empty + stage);
+                        if (kb == n_kblk - 1) umma_commit(tfull + as);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+    } else {
+        const int ew = warp - 2;
+        const int lg = warp & 3;                 // TMEM lane group this warp may read
+        const int q = ew >> 2;                   // column quarter of every tile handled by this warp
+        const int r_in_blk = lg * 32 + lane;
+        const int kk = P.topk;
+        const size_t list0 = (((size_t)blockIdx.x * BM + lg * 32) * 4 + q) * CAPG;   // lane 0's list of this warp
+        float *lv = PP.lv + list0 + (size_t)lane * 4 * CAPG;
+        int *li = PP.li + list0 + (size_t)lane * 4 * CAPG;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x) {
+            const int row = mb * BM + r_in_blk;
+            float thr = -INFINITY;
+            int cnt = 0;
+            long long hlo = 0, hhi = 0;
+            if (P.row_ids != nullptr && row < P.M) {
+                const long long id = P.row_ids[row];
+                hlo = P.hist_ptr[id];
+                hhi = P.hist_ptr[id + 1];
+            }
+            for (int nb = 0; nb < n_nblk; ++nb) {
+                mbar_wait(tfull + as, aphase);
+                tc_fence_after();
+                const uint32_t shared_key = thr_key[r_in_blk];
+                if (shared_key != 0u) thr = fmaxf(thr, key_value(shared_key));
+                const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
+#pragma unroll 1
+                for (int c = 2 * q; c < 2 * q + 2; ++c) {
+                    float r[32];
+                    tmem_ld32(tbase + c * 32, r);
+                    const int col0 = nb * BN + c * 32;
+                    if (col0 >= P.N) break;
+                    if (P.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = col0 + j;
+                            r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
+                        }
+                    } else if (P.scale != 1.f) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] *= P.scale;
+                    }
+                    float mx = fmaxf(r[0], r[1]);
+#pragma unroll
+                    for (int j = 2; j < 32; j += 2) mx = fmaxf(fmaxf(r[j], r[j + 1]), mx);
+                    if (!__any_sync(0xffffffffu, mx > thr)) continue;
+                    const int valid = min(32, P.N - col0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const bool p = (j < valid) && (r[j] > thr);
+                        if (__any_sync(0xffffffffu, p)) {
+                            if (p && (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col0 + j))) {
+                                __stcg(lv + cnt, r[j]);
+                                __stcg(li + cnt, col0 + j);
+                                ++cnt;
+                            }
+                        }
+                    }
+                    uint32_t need = __ballot_sync(0xffffffffu, cnt > CAPG - 32);
+                    if (need) { __threadfence_block(); __syncwarp(); }
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+                        const float t_new = warp_prune_g(PP.lv + list0 + (size_t)src * 4 * CAPG,
+                                                         PP.li + list0 + (size_t)src * 4 * CAPG, c_src, kk, lane);
+                        if (lane == src) {
+                            thr = fmaxf(thr, t_new);
+                            cnt = kk;
+                            atomicMax(thr_key + r_in_blk, order_key(t_new));   // a bound every quarter of the row may use
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + as);
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            }
+            // ---- end of the row block: trim own lists to k, publish counts, merge the four quarters per row
+            {
+                uint32_t need = __ballot_sync(0xffffffffu, cnt > kk);
+                if (need) { __threadfence_block(); __syncwarp(); }
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+                    warp_prune_g(PP.lv + list0 + (size_t)src * 4 * CAPG, PP.li + list0 + (size_t)src * 4 * CAPG, c_src, kk, lane);
+                    if (lane == src) cnt = kk;
+                }
+            }
+            cnt_s[r_in_blk * 4 + q] = cnt;
+            __threadfence_block();
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "r"(128) : "memory");
+            for (int rr = 0; rr < 8; ++rr) {
+                const int rib = lg * 32 + q * 8 + rr;
+                const int orow = mb * BM + rib;
+                if (orow >= P.M) break;
+                const int c0 = cnt_s[rib * 4], c1 = cnt_s[rib * 4 + 1], c2 = cnt_s[rib * 4 + 2], c3 = cnt_s[rib * 4 + 3];
+                const int total = c0 + c1 + c2 + c3;       // <= 4 kk <= 256
+                const size_t rbase = ((size_t)blockIdx.x * BM + rib) * 4 * CAPG;
+                float v[8];
+                int ix[8];
+                uint32_t key[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    int e = lane + 32 * t;
+                    const bool ok = e < total;
+                    int qq = 0;
+                    if (e >= c0) { e -= c0; qq = 1; if (e >= c1) { e -= c1; qq = 2; if (e >= c2) { e -= c2; qq = 3; } } }
+                    v[t] = ok ? __ldcg(PP.lv + rbase + (size_t)qq * CAPG + e) : 0.f;
+                    ix[t] = ok ? __ldcg(PP.li + rbase + (size_t)qq * CAPG + e) : -1;
+                    key[t] = ok ? order_key(v[t]) : 0u;
+                }
+                if (total > kk) {          // keep exactly the kk best (radix select on the keys)
+                    uint32_t Tk = 0;
+                    for (int bit = 31; bit >= 0; --bit) {
+                        const uint32_t c = Tk | (1u << bit);
+                        int n = 0;
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) n += __popc(__ballot_sync(0xffffffffu, key[t] >= c));
+                        if (n >= kk) Tk = c;
+                    }
+                    int g = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) g += __popc(__ballot_sync(0xffffffffu, key[t] > Tk));
+                    int need_eq = kk - g;
+                    const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const bool is_eq = key[t] == Tk && ix[t] >= 0;
+                        const uint32_t me = __ballot_sync(0xffffffffu, is_eq);
+                        const bool keep = key[t] > Tk || (is_eq && __popc(me & below) < need_eq);
+                        need_eq -= min(need_eq, __popc(me));
+                        if (!keep) ix[t] = -1;
+                    }
+                }
+                for (int o = 0; o < kk; ++o) {
+                    float bv = -INFINITY;
+                    int bi = 0x7fffffff;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (ix[t] >= 0 && (bi == 0x7fffffff || v[t] > bv || (v[t] == bv && ix[t] < bi))) { bv = v[t]; bi = ix[t]; }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+                    }
+                    if (lane == 0) {
+                        P.out_val[(size_t)orow * kk + o] = bi == 0x7fffffff ? -INFINITY : bv;
+                        P.out_idx[(size_t)orow * kk + o] = bi == 0x7fffffff ? -1 : bi;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (ix[t] == bi) ix[t] = -1;
+                }
+            }
+            if (q == 0) thr_key[r_in_blk] = 0u;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "r"(128) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -455,10 +765,15 @@ extern "C" int fr_f32_to_bf16(const float *x, void *y, int64_t rows, int32_t d, 
     return fr::check_launch("fr_f32_to_bf16");
 }
 
+extern "C" int64_t fr_gemm_topk_ws_bytes(int32_t M) {
+    const int n_mblk = (M + BM - 1) / BM;
+    return (int64_t)std::min(n_mblk, fr::num_sms()) * BM * 4 * CAPG * 8;
+}
+
 extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_t N, int32_t K, float scale,
                                  const float *bias, const int64_t *row_ids, const int64_t *hist_ptr,
                                  const int32_t *hist_idx, int32_t topk, float *out_val, int32_t *out_idx,
-                                 void *stream) {
+                                 void *ws, int64_t ws_bytes, void *stream) {
     FR_REQUIRE(M >= 0 && N > 0 && K > 0, "fr_gemm_topk_bf16: M=%d N=%d K=%d", M, N, K);
     if (M == 0) return FR_OK;
     FR_REQUIRE(A && B && out_val && out_idx, "fr_gemm_topk_bf16: null pointer");
@@ -482,6 +797,29 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
     Params P{M, N, K, topk, scale, bias, row_ids, hist_ptr, hist_idx, out_val, out_idx};
     const int n_mblk = (M + BM - 1) / BM;
     const int grid = std::min(n_mblk, fr::num_sms());
+    static int impl = -1;
+    if (impl < 0) {
+        const char *e = getenv("FR_TOPK_IMPL");
+        impl = e ? atoi(e) : 2;
+    }
+    if (impl == 2) {
+        const int64_t need = (int64_t)grid * BM * 4 * CAPG * 8;
+        FR_REQUIRE(ws != nullptr && ws_bytes >= need, "fr_gemm_topk_bf16: workspace of %lld bytes required (got %lld)",
+                   (long long)need, (long long)ws_bytes);
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
+            if (e != cudaSuccess) {
+                fr::set_error("fr_gemm_topk_bf16: cannot reserve %d bytes of shared memory: %s", SMEM2, cudaGetErrorString(e));
+                return FR_ECUDA;
+            }
+            attr2 = true;
+        }
+        Params2 P2{P, reinterpret_cast<float *>(ws), reinterpret_cast<int *>(reinterpret_cast<float *>(ws) + (size_t)grid * BM * 4 * CAPG)};
+        fr::LaunchTimer _lt2("gemm_topk_kernel_v2", (cudaStream_t)stream);
+        gemm_topk_kernel_v2<<<grid, THREADS2, SMEM2, (cudaStream_t)stream>>>(ma, mb, P2);
+        return fr::check_launch("fr_gemm_topk_bf16(v2)");
+    }
     fr::LaunchTimer _lt("gemm_topk_kernel", (cudaStream_t)stream);
     gemm_topk_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, P);
     return fr::check_launch("fr_gemm_topk_bf16");

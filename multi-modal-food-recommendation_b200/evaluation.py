@@ -37,6 +37,18 @@ class HistoryCSR:
         self.idx = torch.from_numpy(self.idx_host).to(device)
 
 
+_WS = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    """Scratch for the per-(row, quarter) candidate lists of the ranking kernel (reused across calls)."""
+    ws = _WS.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WS[device] = ws
+    return ws
+
+
 def to_bf16(x: torch.Tensor, l2_normalise: bool = False) -> torch.Tensor:
     x = x.detach()
     if x.dtype != torch.float32 or not x.is_contiguous():
@@ -80,6 +92,7 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
         row_ids = row_ids.to(torch.int64).contiguous()
     if bias is not None:
         bias = bias.detach().float().contiguous()
+    ws = _workspace(dev, int(_L.fr_gemm_topk_ws_bytes(M)))
     prof = PROFILE
     if prof is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
@@ -88,7 +101,7 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
         Ab.data_ptr(), M, Bb.data_ptr(), N, K, float(scale), _lib.ptr(bias),
         _lib.ptr(row_ids) if hist is not None else None, hist.ptr.data_ptr() if hist is not None else None,
         hist.idx.data_ptr() if hist is not None else None, kc, cand_v.data_ptr(), cand_i.data_ptr(),
-        _lib.stream_ptr()), "fr_gemm_topk_bf16")
+        ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "fr_gemm_topk_bf16")
     if prof is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()

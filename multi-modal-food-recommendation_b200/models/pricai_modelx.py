@@ -90,7 +90,10 @@ class PRICAI_ModelX(DotProductRecommender):
         I = self.n_items
         item_w = self.item_embedding.weight
         cur = torch.cuda.current_stream()
-        s1, s2 = self._side_streams()
+        if getattr(self, "fork_streams", True):
+            s1, s2 = self._side_streams()
+        else:                       # serial execution (per-kernel timing in bench.py)
+            s1 = s2 = cur
         s1.wait_stream(cur)
         s2.wait_stream(cur)
         ing = ops.propagate_mean(self.g_ingre, torch.cat((item_w, self.ingre_embedding.weight[:-1]), 0),
@@ -141,8 +144,9 @@ class PRICAI_ModelX(DotProductRecommender):
                                        [(uw, user), (iw, pos_item), (iw, neg_item)],
                                        reg_den=float(neg_item.shape[0]), gamma=self.mf_loss.gamma)
         cur = torch.cuda.current_stream()
-        cur.wait_stream(self._side_streams()[0])
-        cl_loss.record_stream(cur)
+        if getattr(self, "fork_streams", True):
+            cur.wait_stream(self._side_streams()[0])
+            cl_loss.record_stream(cur)
         return mf_loss_g, self.loss_cl * cl_loss, (self.reg_weight * reg).reshape(1)
 
     def CL_loss(self, hidden, hidden_norm=True, temperature=0.5):

@@ -31,9 +31,11 @@ def main():
     Ub, Ib = E.to_bf16(U), E.to_bf16(I)
     cv = torch.empty(M, 32, device="cuda"); ci = torch.empty(M, 32, dtype=torch.int32, device="cuda")
 
+    ws = E._workspace(U.device, int(_lib.lib.fr_gemm_topk_ws_bytes(M)))
+
     def raw():
         _lib.check(_lib.lib.fr_gemm_topk_bf16(Ub.data_ptr(), M, Ib.data_ptr(), N, K, 1.0, None, None, None, None, 32,
-                                              cv.data_ptr(), ci.data_ptr(), _lib.stream_ptr()))
+                                              cv.data_ptr(), ci.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
     t_raw = timeit(raw)
     t_full = timeit(lambda: E.gemm_topk(U, I, k))
     res = {"M": M, "N": N, "K": K, "gemm_topk_ms": t_raw, "tflops": 2.0 * M * N * K / t_raw / 1e9,

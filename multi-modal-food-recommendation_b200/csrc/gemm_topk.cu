@@ -189,6 +189,8 @@ __device__ __noinline__ float warp_prune(uint32_t bv, uint32_t bi, int cnt, int 
     return key_value(T);
 }
 
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
 __device__ __forceinline__ bool in_history(const int32_t *h, long long lo, long long hi, int col) {
     while (lo < hi) {
         const long long mid = (lo + hi) >> 1;
@@ -548,7 +550,8 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 hhi = P.hist_ptr[id + 1];
             }
             for (int nb = 0; nb < n_nblk; ++nb) {
-                mbar_wait(tfull + as, aphase);
+                if (lane == 0) mbar_wait(tfull + as, aphase);   // one poller per warp; the rest park at the syncwarp
+                __syncwarp();
                 tc_fence_after();
                 const uint32_t shared_key = thr_key[r_in_blk];
                 if (shared_key != 0u) thr = fmaxf(thr, key_value(shared_key));
@@ -569,22 +572,33 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) r[j] *= P.scale;
                     }
-                    float mx = fmaxf(r[0], r[1]);
+                    // hot path: 3-input max tree over four 8-column groups, one compare per 32 scores
+                    float g[4];
 #pragma unroll
-                    for (int j = 2; j < 32; j += 2) mx = fmaxf(fmaxf(r[j], r[j + 1]), mx);
-                    if (!__any_sync(0xffffffffu, mx > thr)) continue;
-                    const int valid = min(32, P.N - col0);
+                    for (int gq = 0; gq < 4; ++gq)
+                        g[gq] = max3(max3(r[8 * gq], r[8 * gq + 1], r[8 * gq + 2]),
+                                     max3(r[8 * gq + 3], r[8 * gq + 4], r[8 * gq + 5]), fmaxf(r[8 * gq + 6], r[8 * gq + 7]));
+                    const float mx = fmaxf(max3(g[0], g[1], g[2]), g[3]);
+                    if (mx > thr) {
+                        // only the lanes (rows) that have a candidate come here, and each walks only the
+                        // 8-column groups that hold one: the cost follows the number of candidates
+                        const int valid = min(32, P.N - col0);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const bool p = (j < valid) && (r[j] > thr);
-                        if (__any_sync(0xffffffffu, p)) {
-                            if (p && (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col0 + j))) {
-                                __stcg(lv + cnt, r[j]);
-                                __stcg(li + cnt, col0 + j);
-                                ++cnt;
+                        for (int gq = 0; gq < 4; ++gq) {
+                            if (g[gq] > thr) {
+#pragma unroll
+                                for (int j = 8 * gq; j < 8 * gq + 8; ++j) {
+                                    if (j < valid && r[j] > thr &&
+                                        (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col0 + j))) {
+                                        __stcg(lv + cnt, r[j]);
+                                        __stcg(li + cnt, col0 + j);
+                                        ++cnt;
+                                    }
+                                }
                             }
                         }
                     }
+                    __syncwarp();
                     uint32_t need = __ballot_sync(0xffffffffu, cnt > CAPG - 32);
                     if (need) { __threadfence_block(); __syncwarp(); }
                     while (need) {

@@ -400,11 +400,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // a row share the best known lower bound of the row's k-th score through a shared-memory key
 // (atomicMax at prune time), and their lists are merged, selected and sorted per row at the end of the
 // row block.
+// Two sweeps per row block (the MMA pipe is idle > 90 % of the time, so recomputing the tiles is free):
+//   pass 0 (bounding): branch-free -- per (row, quarter) the running maximum of NG column groups goes to
+//          shared memory (atomicMax on order-preserving keys).  The (k + h)-th largest group maximum T
+//          (h = the row's history length, because a masked column may hold a group's maximum) is a lower
+//          bound of the k-th eligible score: at least k eligible scores are >= T.
+//   pass 1 (collection): the streaming top-k above, started from threshold T instead of -inf, so only
+//          ~k scores per row ever take the candidate path.
 constexpr int EW2 = 16;
 constexpr int THREADS2 = 64 + EW2 * 32;
-constexpr int STAGES2 = 4;
+constexpr int STAGES2 = 3;
+constexpr int NG = 128;                        // column groups per row for the bounding pass
 constexpr int CAPG = 96;                       // slots per (row, quarter) list; prune when > CAPG - 32
-constexpr int SMEM2 = 1024 + STAGES2 * STAGE_BYTES + BM * 4 * 4 + BM * 4 + 256;
+constexpr int SMEM2 = 1024 + STAGES2 * STAGE_BYTES + BM * 4 * 4 + BM * 4 + NG * BM * 4 + 256;
 
 __device__ __noinline__ float warp_prune_g(float *bv, int *bi, int cnt, int k, int lane) {
     constexpr int T = CAPG / 32;
@@ -456,6 +464,7 @@ struct Params2 {
     Params p;
     float *lv;   // [grid][BM][4][CAPG]
     int *li;
+    int two_pass;
 };
 
 __global__ void __launch_bounds__(THREADS2, 1)
@@ -466,12 +475,14 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t *tiles = smem;
     int *cnt_s = reinterpret_cast<int *>(smem + STAGES2 * STAGE_BYTES);   // [BM][4]
     uint32_t *thr_key = reinterpret_cast<uint32_t *>(cnt_s + BM * 4);      // [BM] best known k-th key per row
-    uint64_t *bars = reinterpret_cast<uint64_t *>(((uintptr_t)(thr_key + BM) + 7) & ~(uintptr_t)7);
+    uint32_t *gkey = thr_key + BM;                                         // [NG][BM] group maxima (pass 0)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(((uintptr_t)(gkey + NG * BM) + 7) & ~(uintptr_t)7);
     uint64_t *full = bars, *empty = bars + STAGES2, *tfull = bars + 2 * STAGES2, *tempty = bars + 2 * STAGES2 + ACC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES2 + 2 * ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_mblk = (P.M + BM - 1) / BM, n_nblk = (P.N + BN - 1) / BN, n_kblk = (P.K + BK - 1) / BK;
+    const int n_pass = PP.two_pass ? 2 : 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -479,6 +490,7 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < BM) thr_key[threadIdx.x] = 0u;
+    for (int i = threadIdx.x; i < NG * BM; i += THREADS2) gkey[i] = 0u;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -493,6 +505,7 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x)
+              for (int pass = 0; pass < n_pass; ++pass)
                 for (int nb = 0; nb < n_nblk; ++nb)
                     for (int kb = 0; kb < n_kblk; ++kb) {
                         mbar_wait(empty + stage, phase ^ 1);
@@ -507,6 +520,7 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
         for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x)
+          for (int pass = 0; pass < n_pass; ++pass)
             for (int nb = 0; nb < n_nblk; ++nb) {
                 if (lane == 0) mbar_wait(tempty + as, aphase ^ 1);
                 __syncwarp();
@@ -548,6 +562,92 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const long long id = P.row_ids[row];
                 hlo = P.hist_ptr[id];
                 hhi = P.hist_ptr[id + 1];
+            }
+            if (n_pass == 2) {
+                // ---------------- pass 0: group maxima -> lower bound of the k-th eligible score
+                float gmax = -INFINITY;
+                int gcur = 0;
+                for (int nb = 0; nb < n_nblk; ++nb) {
+                    if (lane == 0) mbar_wait(tfull + as, aphase);
+                    __syncwarp();
+                    tc_fence_after();
+                    const int gid = (int)(((long long)(nb * 4 + q) * NG) / (4LL * n_nblk));
+                    if (gid != gcur) {
+                        if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
+                        gmax = -INFINITY;
+                        gcur = gid;
+                    }
+                    const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + as * BN;
+#pragma unroll 1
+                    for (int c = 2 * q; c < 2 * q + 2; ++c) {
+                        float r[32];
+                        tmem_ld32(tbase + c * 32, r);
+                        const int col0 = nb * BN + c * 32;
+                        if (col0 >= P.N) break;
+                        if (P.bias != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int col = col0 + j;
+                                r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
+                            }
+                        } else if (P.scale != 1.f) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] *= P.scale;
+                        }
+                        if (col0 + 32 > P.N) {          // zero-filled columns past N must not bound anything
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j >= P.N) r[j] = -INFINITY;
+                        }
+                        float m0 = max3(r[0], r[1], r[2]), m1 = max3(r[3], r[4], r[5]);
+#pragma unroll
+                        for (int j = 6; j < 30; j += 6) {
+                            m0 = max3(m0, r[j], r[j + 1]);
+                            m1 = max3(m1, r[j + 2], r[j + 3]);
+                            m0 = fmaxf(m0, r[j + 4]);
+                            m1 = fmaxf(m1, r[j + 5]);
+                        }
+                        gmax = fmaxf(gmax, max3(m0, m1, fmaxf(r[30], r[31])));
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + as);
+                    if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+                }
+                if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
+                __threadfence_block();
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "r"(128) : "memory");
+                // warp q of the lane group bounds rows q*8 .. q*8+7: the (k + h)-th largest of NG group maxima
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int rib = lg * 32 + q * 8 + rr;
+                    uint32_t key[NG / 32];
+#pragma unroll
+                    for (int t = 0; t < NG / 32; ++t) {
+                        key[t] = gkey[(lane + 32 * t) * BM + rib];
+                        gkey[(lane + 32 * t) * BM + rib] = 0u;       // ready for the next row block
+                    }
+                    int h = 0;
+                    const int orow = mb * BM + rib;
+                    if (P.row_ids != nullptr && orow < P.M) {
+                        const long long id = P.row_ids[orow];
+                        { const long long hl = P.hist_ptr[id + 1] - P.hist_ptr[id]; h = hl > NG ? NG : (int)hl; }
+                    }
+                    const int want = kk + h;
+                    uint32_t Tk = 0;
+                    if (want <= NG) {
+                        for (int bit = 31; bit >= 0; --bit) {
+                            const uint32_t c = Tk | (1u << bit);
+                            int n = 0;
+#pragma unroll
+                            for (int t = 0; t < NG / 32; ++t) n += __popc(__ballot_sync(0xffffffffu, key[t] >= c));
+                            if (n >= want) Tk = c;
+                        }
+                    }
+                    // collection accepts `score > thr`: publish the key just below T so that ties with T pass
+                    if (lane == 0) thr_key[rib] = Tk > 1u ? Tk - 1u : 0u;
+                }
+                __threadfence_block();
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "r"(128) : "memory");
             }
             for (int nb = 0; nb < n_nblk; ++nb) {
                 if (lane == 0) mbar_wait(tfull + as, aphase);   // one poller per warp; the rest park at the syncwarp
@@ -829,7 +929,13 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
             }
             attr2 = true;
         }
-        Params2 P2{P, reinterpret_cast<float *>(ws), reinterpret_cast<int *>(reinterpret_cast<float *>(ws) + (size_t)grid * BM * 4 * CAPG)};
+        static int two_pass = -1;
+        if (two_pass < 0) {
+            const char *e = getenv("FR_TOPK_TWO_PASS");
+            two_pass = e ? atoi(e) : 1;
+        }
+        Params2 P2{P, reinterpret_cast<float *>(ws),
+                   reinterpret_cast<int *>(reinterpret_cast<float *>(ws) + (size_t)grid * BM * 4 * CAPG), two_pass};
         fr::LaunchTimer _lt2("gemm_topk_kernel_v2", (cudaStream_t)stream);
         gemm_topk_kernel_v2<<<grid, THREADS2, SMEM2, (cudaStream_t)stream>>>(ma, mb, P2);
         return fr::check_launch("fr_gemm_topk_bf16(v2)");

@@ -28,7 +28,7 @@ extern "C" {
 #define FR_EUNSUPPORTED (-2) /* shape outside what the kernels are specialised for                  */
 #define FR_ECUDA (-3)        /* CUDA runtime error at launch                                        */
 
-#define FR_SPMM_SEG 128 /* max nnz per propagation segment (see fr_spmm_plan_*) */
+#define FR_SPMM_SEG 128 /* largest allowed `seg_len` (nnz per propagation segment, see fr_spmm_plan_*) */
 
 int fr_version(void);
 const char *fr_last_error(void);
@@ -47,7 +47,7 @@ int fr_profile_dump(char *buf, int64_t cap);
  * mean_l S^l E0 = (E0 + S(E0 + S(...)))/(L+1)).  The backward of `torch.sparse.mm` w.r.t. X is the
  * same call on the CSR of S^T (== S for the symmetric normalised adjacencies).
  *
- * Rows are processed as SEGMENTS of at most FR_SPMM_SEG nonzeros so that one popular item cannot
+ * Rows are processed as SEGMENTS of at most `seg_len` (<= FR_SPMM_SEG) nonzeros so that one popular item cannot
  * serialise a warp; rows longer than a segment are reduced deterministically (fixed order) by the
  * last segment to finish.  The segment plan is built once per graph:
  *
@@ -63,9 +63,10 @@ int fr_profile_dump(char *buf, int64_t cap);
  * adjacency incl. self loops, X = lin(x)).
  * d must be 32, 64 or 128.
  */
-int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, int64_t *n_seg, int64_t *n_long,
-                       int64_t *n_part);
-int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, int32_t *seg_host, int32_t *long_rows_host);
+int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, int32_t seg_len, int64_t *n_seg,
+                       int64_t *n_long, int64_t *n_part);
+int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, int32_t seg_len, int32_t *seg_host,
+                      int32_t *long_rows_host);
 int fr_spmm_csr_f32(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
                     const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z,
                     float alpha, float beta, const float *bias, int32_t act, float *Y, float *partial,

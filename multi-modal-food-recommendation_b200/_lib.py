@@ -35,8 +35,8 @@ SIGNATURES = {
     "fr_launch_count": (_i64, []),
     "fr_profile_enable": (C.c_int, [C.c_int]),
     "fr_profile_dump": (C.c_int, [C.c_char_p, _i64]),
-    "fr_spmm_plan_sizes": (C.c_int, [_p, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
-    "fr_spmm_plan_fill": (C.c_int, [_p, _i32, _p, _p]),
+    "fr_spmm_plan_sizes": (C.c_int, [_p, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "fr_spmm_plan_fill": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "fr_spmm_csr_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i32, _p, _p, _f32, _f32, _p, _i32, _p, _p, _p, _p]),
     "fr_rank_loss_ws_floats": (_i64, []),
     "fr_rank_loss_fwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),

@@ -381,7 +381,16 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
 #pragma unroll
     for (int t = 0; t < VPL; ++t) {
         float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(partial + ((size_t)lr.z + k) * D + 4 * (lg + LPR * t)));
+        const float *pp = partial + (size_t)lr.z * D + 4 * (lg + LPR * t);
+        int k = 0;
+        for (; k + 8 <= lr.y; k += 8) {          // eight partial rows in flight; the fold order stays k = 0, 1, 2, ...
+            float4 p8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) p8[u] = fr::ldcg_f4(pp + (size_t)(k + u) * D);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) fr::add4(tot, p8[u]);
+        }
+        for (; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(pp + (size_t)k * D));
         epilogue_store<D, ACT>(tot, lr.w, 4 * (lg + LPR * t), Z, alpha, beta, bias, Y);
     }
     if (lg == 0) counters[s.w] = 0;
@@ -488,11 +497,11 @@ struct PlanCounts {
     int64_t n_seg = 0, n_long = 0, n_part = 0;
 };
 
-PlanCounts count_plan(const int32_t *rp, int32_t n_rows) {
+PlanCounts count_plan(const int32_t *rp, int32_t n_rows, int64_t SEG) {
     PlanCounts c;
     for (int32_t r = 0; r < n_rows; ++r) {
         const int64_t deg = (int64_t)rp[r + 1] - rp[r];
-        const int64_t k = deg <= FR_SPMM_SEG ? 1 : (deg + FR_SPMM_SEG - 1) / FR_SPMM_SEG;
+        const int64_t k = deg <= SEG ? 1 : (deg + SEG - 1) / SEG;
         c.n_seg += k;
         if (k > 1) {
             c.n_long += 1;
@@ -504,12 +513,13 @@ PlanCounts count_plan(const int32_t *rp, int32_t n_rows) {
 
 }  // namespace
 
-extern "C" int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, int64_t *n_seg, int64_t *n_long,
-                                  int64_t *n_part) {
+extern "C" int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, int32_t seg_len, int64_t *n_seg,
+                                  int64_t *n_long, int64_t *n_part) {
     FR_REQUIRE(row_ptr_host && n_seg && n_long && n_part && n_rows >= 0, "fr_spmm_plan_sizes: bad argument");
+    FR_REQUIRE(seg_len >= 8 && seg_len <= FR_SPMM_SEG, "fr_spmm_plan_sizes: seg_len=%d outside [8, %d]", seg_len, FR_SPMM_SEG);
     for (int32_t r = 0; r < n_rows; ++r)
         FR_REQUIRE(row_ptr_host[r + 1] >= row_ptr_host[r], "fr_spmm_plan_sizes: row_ptr not monotone at %d", r);
-    const PlanCounts c = count_plan(row_ptr_host, n_rows);
+    const PlanCounts c = count_plan(row_ptr_host, n_rows, seg_len);
     *n_seg = c.n_seg;
     *n_long = c.n_long;
     *n_part = c.n_part;
@@ -519,16 +529,18 @@ extern "C" int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, i
 // Segment order: every long-row segment first (they are the critical path: the last one also
 // performs the reduction), then whole-row segments by descending length (longest-first keeps the
 // tail of the launch short); ties keep row order so neighbouring rows stay neighbours.
-extern "C" int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, int32_t *seg_host,
+extern "C" int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, int32_t seg_len, int32_t *seg_host,
                                  int32_t *long_rows_host) {
     FR_REQUIRE(row_ptr_host && seg_host && n_rows >= 0, "fr_spmm_plan_fill: bad argument");
+    FR_REQUIRE(seg_len >= 8 && seg_len <= FR_SPMM_SEG, "fr_spmm_plan_fill: seg_len=%d outside [8, %d]", seg_len, FR_SPMM_SEG);
+    const int64_t SEG = seg_len;
     const int32_t *rp = row_ptr_host;
     int64_t s = 0, nl = 0, pb = 0;
     for (int32_t r = 0; r < n_rows; ++r) {
         const int64_t deg = (int64_t)rp[r + 1] - rp[r];
-        if (deg <= FR_SPMM_SEG) continue;
+        if (deg <= SEG) continue;
         FR_REQUIRE(long_rows_host, "fr_spmm_plan_fill: long_rows_host is null but row %d is long", r);
-        const int64_t k = (deg + FR_SPMM_SEG - 1) / FR_SPMM_SEG;
+        const int64_t k = (deg + SEG - 1) / SEG;
         int32_t *lr = long_rows_host + 4 * nl;
         lr[0] = (int32_t)s;
         lr[1] = (int32_t)k;
@@ -537,24 +549,24 @@ extern "C" int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, in
         for (int64_t i = 0; i < k; ++i, ++s) {
             int32_t *q = seg_host + 4 * s;
             q[0] = r;
-            q[1] = rp[r] + (int32_t)(i * FR_SPMM_SEG);
-            q[2] = (int32_t)std::min<int64_t>(FR_SPMM_SEG, deg - i * FR_SPMM_SEG);
+            q[1] = rp[r] + (int32_t)(i * SEG);
+            q[2] = (int32_t)std::min<int64_t>(SEG, deg - i * SEG);
             q[3] = (int32_t)nl;
         }
         pb += k;
         ++nl;
     }
     // counting sort of the remaining rows by descending degree
-    std::vector<int64_t> start(FR_SPMM_SEG + 2, 0);
+    std::vector<int64_t> start((size_t)SEG + 2, 0);
     for (int32_t r = 0; r < n_rows; ++r) {
         const int64_t deg = (int64_t)rp[r + 1] - rp[r];
-        if (deg <= FR_SPMM_SEG) start[FR_SPMM_SEG - deg + 1] += 1;
+        if (deg <= SEG) start[SEG - deg + 1] += 1;
     }
-    for (int i = 1; i <= FR_SPMM_SEG + 1; ++i) start[i] += start[i - 1];
+    for (int i = 1; i <= SEG + 1; ++i) start[i] += start[i - 1];
     for (int32_t r = 0; r < n_rows; ++r) {
         const int64_t deg = (int64_t)rp[r + 1] - rp[r];
-        if (deg > FR_SPMM_SEG) continue;
-        int32_t *q = seg_host + 4 * (s + start[FR_SPMM_SEG - deg]++);
+        if (deg > SEG) continue;
+        int32_t *q = seg_host + 4 * (s + start[SEG - deg]++);
         q[0] = r;
         q[1] = rp[r];
         q[2] = (int32_t)deg;

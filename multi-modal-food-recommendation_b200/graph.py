@@ -13,13 +13,14 @@ multiplies scipy matrices on every model construction; the values produced here 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
 
 from . import _lib
 
-SEG = 128  # FR_SPMM_SEG
+SEG = int(os.environ.get("FR_SPMM_SEG", "32"))  # nonzeros per segment (<= FR_SPMM_SEG = 128)
 
 
 class PropGraph:
@@ -32,12 +33,12 @@ class PropGraph:
         self.device = torch.device(device)
         self.row_ptr_host = row_ptr
         n_seg, n_long, n_part = C.c_int64(), C.c_int64(), C.c_int64()
-        _lib.check(_lib.lib.fr_spmm_plan_sizes(row_ptr.ctypes.data, self.n_rows, C.byref(n_seg), C.byref(n_long),
+        _lib.check(_lib.lib.fr_spmm_plan_sizes(row_ptr.ctypes.data, self.n_rows, SEG, C.byref(n_seg), C.byref(n_long),
                                                C.byref(n_part)), "fr_spmm_plan_sizes")
         self.n_seg, self.n_long, self.n_part = n_seg.value, n_long.value, n_part.value
         seg = np.empty((max(self.n_seg, 1), 4), dtype=np.int32)
         lrows = np.empty((max(self.n_long, 1), 4), dtype=np.int32)
-        _lib.check(_lib.lib.fr_spmm_plan_fill(row_ptr.ctypes.data, self.n_rows, seg.ctypes.data, lrows.ctypes.data),
+        _lib.check(_lib.lib.fr_spmm_plan_fill(row_ptr.ctypes.data, self.n_rows, SEG, seg.ctypes.data, lrows.ctypes.data),
                    "fr_spmm_plan_fill")
         self.seg_host, self.long_rows_host = seg, lrows
         dev = self.device

@@ -29,7 +29,7 @@ def test_error_reporting_without_gpu():
     import ctypes as C
     rp = np.array([0, 3, 2], dtype=np.int32)  # not monotone
     a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
-    rc = _lib.lib.fr_spmm_plan_sizes(rp.ctypes.data, 2, C.byref(a), C.byref(b), C.byref(c))
+    rc = _lib.lib.fr_spmm_plan_sizes(rp.ctypes.data, 2, 32, C.byref(a), C.byref(b), C.byref(c))
     assert rc == -1
     assert b"monotone" in _lib.lib.fr_last_error()
     with pytest.raises(_lib.FoodRecError):

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 
-SEG = int(os.environ.get("FR_SPMM_SEG", "32"))  # nonzeros per segment (<= FR_SPMM_SEG = 128)
+SEG = int(os.environ.get("FR_SPMM_SEG", "64"))  # nonzeros per segment (<= FR_SPMM_SEG = 128)
 
 
 class PropGraph:

@@ -76,3 +76,30 @@ def test_by_user_candidate_scoring(mini_ds):
         m.user_embedding.weight.mul_(2.0)
         s2 = m.inference_by_user({"user_input": users.cuda(), "item_input": cand.cuda()})
     assert not torch.allclose(s1, s2)
+
+
+def test_schgn_graphconv_block_vs_oracle(mini_ds):
+    """SCHGN's `GraphConv` (GCNConv + tanh) on the heterogeneous user/item/ingredient/calorie graph."""
+    from foodrec_b200.models.schgn_gcn import GraphConv
+    from oracle import adjacency, propagation
+    ds = mini_ds
+    n = ds.n_users + ds.n_items + ds.num_ingredients + ds.num_calories_level
+    ei = adjacency.schgn_edge_index(ds)
+    src, dst, w = adjacency.gcn_norm_edges(ei, n)
+    torch.manual_seed(4)
+    conv = GraphConv(64, 64).cuda()
+    assert sorted(conv.state_dict().keys()) == ["conv1.bias", "conv1.lin.weight"]
+    x = (torch.randn(n, 64) * 0.1).requires_grad_(True)
+    t = torch.randn(n, 64)
+    W, b = conv.conv1.lin.weight.detach().cpu().clone().requires_grad_(True), conv.conv1.bias.detach().cpu().clone().requires_grad_(True)
+    ref = propagation.gcn_conv_tanh(x, src, dst, w, W, b)
+    (ref * t).sum().backward()
+    xd = x.detach().cuda().requires_grad_(True)
+    out = conv(xd, ei.cuda())
+    (out * t.cuda()).sum().backward()
+    close(out, ref.detach().numpy())
+    close(xd.grad, x.grad.numpy(), rtol=2e-5)
+    close(conv.conv1.lin.weight.grad, W.grad.numpy(), rtol=2e-5)
+    close(conv.conv1.bias.grad, b.grad.numpy(), rtol=2e-5)
+    out2 = conv(xd, ei.cuda())   # second call reuses the cached plan, like the reference's two calls per batch
+    assert torch.equal(out, out2)

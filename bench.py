@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="drop-in eager step (no CUDA graph)")
+    ap.add_argument("--foreach-adam", action="store_true", help="torch's default foreach Adam instead of fused=True")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,9 +201,10 @@ def main():
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     model = model.to(dev)
     model.train()
-    # trainer.py:142-143 builds optim.Adam(params, lr, weight_decay); capturable keeps `step` on the device
+    # trainer.py:142-143 builds optim.Adam(params, lr, weight_decay).  Same optimizer, torch's fused
+    # multi-tensor implementation (one launch instead of ~15), capturable so the step stays on the device.
     opt = torch.optim.Adam(model.parameters(), lr=cfg["learning_rate"], weight_decay=0.0,
-                           capturable=not args.eager)
+                           capturable=not args.eager, fused=not args.foreach_adam)
     n_b = args.steps + args.warmup
     # weak scaling: every rank trains on its own batches of the replicated graph (multi-GPU)
     host_batches = sample_train_batches(ds, BATCH, min(n_b, 64), seed=7 + rank)
@@ -318,7 +320,11 @@ def main():
         "step_mode": step_mode,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "spmm_group_kernel<64,8,4>", "achieved": achieved, "peak": peaks[0],
-                     "unit": "GB/s", "frac": achieved / peaks[0], "traffic": None, "peak_source": peaks[1],
+                     "unit": "GB/s", "frac": achieved / peaks[0], "traffic": _spmm_traffic(), "peak_source": peaks[1],
+                     "traffic_source": "profiles/r1_spmm_step_traffic.json: mean dram read+write bytes per launch, ncu --set "
+                                       "full over the 14 propagation launches of one step (below the algorithmic bytes: "
+                                       "the step's tables stay in the 126 MB L2)",
+                     "algorithmic_bytes_per_launch": tot_bytes / max(n_launch, 1),
                      "launches_per_step": n_launch / 3, "avg_launch_us": tot_ms * 1e3 / max(n_launch, 1),
                      "kernel_share_of_step": tot_ms / 3 / ms_dev},
     }
@@ -404,6 +410,14 @@ def _bench_eval(model, ds, dev, rank, world, barrier):
     return out
 
 
+def _spmm_traffic():
+    p = os.path.join(ROOT, "profiles", "r1_spmm_step_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch_mean"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def _tensor_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -446,7 +460,7 @@ def _working_set_mb(model, opt):
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        return float(json.load(open(p))["hbm_gbs_sustained"] if "hbm_gbs_sustained" in json.load(open(p)) else json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 

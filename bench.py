@@ -286,9 +286,27 @@ def main():
     l1 = _lib.launch_count()
     eager(resident[0])
     launches_per_step_eager = _lib.launch_count() - l1  # kernels of this library per step (graph replays the same)
-    tot_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    tot_bytes = sum(nb for _, _, nb in prof)
-    n_launch = len(prof)
+    # Each of the step's propagation launches (3 eager steps recorded) is re-issued 20x back to back with the
+    # same plan and operand shapes, bracketed by one CUDA-event pair on the launch stream: the stream stays
+    # busy, so the figure is kernel time, not Python launch latency.  Operands stay L2-warm, as inside the step.
+    tot_ms, tot_bytes, n_launch, REP = 0.0, 0.0, len(prof), 20
+    bufs = {}
+    for _, _, nb, g, has_z in prof:
+        key = (g.n_rows, g.n_cols)
+        if key not in bufs:
+            bufs[key] = (torch.randn(g.n_cols, 64, device=dev), torch.randn(g.n_rows, 64, device=dev),
+                         torch.empty(g.n_rows, 64, device=dev))
+        X, Z, Y = bufs[key]
+        ops.spmm(g, X, Z=Z if has_z else None, alpha=0.5, beta=0.5, out=Y)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(REP):
+            ops.spmm(g, X, Z=Z if has_z else None, alpha=0.5, beta=0.5, out=Y)
+        b.record()
+        torch.cuda.synchronize()
+        tot_ms += a.elapsed_time(b) / REP
+        tot_bytes += nb
+    del bufs
     peaks = _peaks()
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
 

@@ -14,7 +14,7 @@ from . import _lib
 from .graph import PropGraph
 
 _L = _lib.lib
-# bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes) per propagation launch
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes, graph, has_z) per propagation launch
 PROFILE = None
 
 
@@ -57,7 +57,7 @@ def spmm(graph: PropGraph, X: torch.Tensor, Z: torch.Tensor | None = None, alpha
     if prof is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
-        prof.append((ev0, ev1, graph.spmm_bytes(d)))
+        prof.append((ev0, ev1, graph.spmm_bytes(d), graph, Z is not None))
     return out
 
 

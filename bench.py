@@ -219,22 +219,28 @@ def main():
         losses = model.calculate_loss(batch)
         loss = sum(losses)
         loss.backward()
-        if world > 1:
+        if world > 1 and hook is None:
             _allreduce_grads(model, world)
+        elif world > 1:
+            hook()
         opt.step()
         return losses
 
+    hook = None
     step_mode = "eager"
     if args.eager:
         step = eager
     else:
-        from foodrec_b200.train import allreduce_mean_grads
-        try:   # N > 1: the NCCL all-reduces of the dense gradients are captured inside the graph
-            step = GraphedTrainStep(model, opt, resident[0], keys=keys,
-                                    grad_hook=allreduce_mean_grads() if world > 1 else None)
+        from foodrec_b200.train import OverlappedGradAllReduce
+        try:   # N > 1: per-gradient NCCL all-reduces on a side stream, captured inside the graph
+            hook = OverlappedGradAllReduce(model) if world > 1 else None
+            step = GraphedTrainStep(model, opt, resident[0], keys=keys, grad_hook=hook)
             step_mode = "cuda_graph_replay"
         except Exception as e:  # noqa: BLE001  (capture of a collective refused: stay eager, say so)
             print(f"[bench] graph capture failed, running eager: {e}", file=sys.stderr)
+            if world > 1 and hook is not None:
+                hook.remove()
+                hook = None
             step = eager
 
     def barrier():

@@ -35,6 +35,34 @@ def allreduce_mean_grads(group=None):
     return hook
 
 
+class OverlappedGradAllReduce:
+    """Data-parallel gradient averaging that overlaps the backward: every parameter's gradient is
+    all-reduced (NCCL, AVG) on a communication stream as soon as autograd has accumulated it, so the
+    user-table gradient (ready after the user-item backward) travels while the item-side graphs are
+    still back-propagating.  Call the object between `backward()` and `optimizer.step()` to join the
+    streams.  Works under CUDA-graph capture (the communication stream becomes a parallel branch)."""
+
+    def __init__(self, model, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        dev = next(model.parameters()).device
+        self.comm = torch.cuda.Stream(device=dev)
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in model.parameters() if p.requires_grad]
+
+    def _hook(self, p):
+        cur = torch.cuda.current_stream()
+        self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):
+            self.dist.all_reduce(p.grad, op=self.dist.ReduceOp.AVG, group=self.group)
+
+    def __call__(self, model=None):
+        torch.cuda.current_stream().wait_stream(self.comm)
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
 class GraphedTrainStep:
     """Capture `zero_grad -> calculate_loss -> backward -> optimizer.step` once, replay per batch.
 

@@ -1,22 +1,21 @@
-"""Parameter initialisers matching FoodRec/common/init.py:7-42 (same RNG consumption order, so the
-same seed yields the same initial `state_dict` as the reference model)."""
+"""Parameter initialisers with the reference's semantics (FoodRec/common/init.py:7-42): the weight
+of every `nn.Embedding` / `nn.Linear` is re-drawn with a Xavier scheme and `nn.Linear` biases are
+zeroed, module by module in `Module.apply` order -- so one seed yields the reference's initial
+`state_dict` (checked bit-for-bit in tests/test_host.py)."""
 import torch.nn as nn
-from torch.nn.init import constant_, xavier_normal_, xavier_uniform_
+from torch.nn import init as _init
 
 
-def xavier_uniform_initialization(module):
-    if isinstance(module, nn.Embedding):
-        xavier_uniform_(module.weight.data)
-    elif isinstance(module, nn.Linear):
-        xavier_uniform_(module.weight.data)
-        if module.bias is not None:
-            constant_(module.bias.data, 0)
+def _make_initializer(draw):
+    def initializer(module):
+        is_linear = isinstance(module, nn.Linear)
+        if not (is_linear or isinstance(module, nn.Embedding)):
+            return
+        draw(module.weight.data)
+        if is_linear and module.bias is not None:
+            _init.constant_(module.bias.data, 0)
+    return initializer
 
 
-def xavier_normal_initialization(module):
-    if isinstance(module, nn.Embedding):
-        xavier_normal_(module.weight.data)
-    elif isinstance(module, nn.Linear):
-        xavier_normal_(module.weight.data)
-        if module.bias is not None:
-            constant_(module.bias.data, 0)
+xavier_uniform_initialization = _make_initializer(_init.xavier_uniform_)
+xavier_normal_initialization = _make_initializer(_init.xavier_normal_)

@@ -1,17 +1,28 @@
-"""Parameter-free loss modules kept so that `str(model)` and attribute names match the reference
-(`self.mf_loss`, `self.reg_loss`; FoodRec/common/loss.py:8-50).  The arithmetic runs in the fused
-kernel behind `ops.rank_loss`; calling these modules directly routes to small fused kernels too."""
-import torch
+"""Parameter-free holders for the loss hyper-parameters.
+
+The reference models own `self.mf_loss = BPRLoss()` and `self.reg_loss = EmbLoss()`
+(FoodRec/common/loss.py:8-50); the drop-ins keep those attributes (so `str(model)` and the module tree
+match) but the arithmetic runs in the fused kernel behind `ops.rank_loss`, which reads `gamma` / `norm`
+from here."""
 import torch.nn as nn
 
 
-class BPRLoss(nn.Module):
+class _Spec(nn.Module):
+    def __init__(self, **hyper):
+        super().__init__()
+        for k, v in hyper.items():
+            setattr(self, k, v)
+
+    def forward(self, *args, **kw):
+        raise RuntimeError(f"{type(self).__name__} is a hyper-parameter holder; the loss is computed by "
+                           "foodrec_b200.ops.rank_loss")
+
+
+class BPRLoss(_Spec):
     def __init__(self, gamma=1e-10):
-        super().__init__()
-        self.gamma = gamma
+        super().__init__(gamma=gamma)
 
 
-class EmbLoss(nn.Module):
+class EmbLoss(_Spec):
     def __init__(self, norm=2):
-        super().__init__()
-        self.norm = norm
+        super().__init__(norm=norm)

@@ -190,3 +190,27 @@ def centroid_topk(features: torch.Tensor, centres: torch.Tensor, k: int = 6, **k
     bias = -0.5 * (c * c).sum(1)
     _, idx = gemm_topk(features, c, k, bias=bias, metric=1, **kw)
     return idx
+
+
+# ------------------------------------------------------------------------------ by-user evaluation
+def evaluate_by_user(model, users, cand_ptr, cand_items, n_pos, neg_num: int = 500):
+    """The reference's default evaluation (`eval_by_user: True`): every user is scored against its
+    positives followed by `neg_num` sampled negatives (FoodRec/common/trainer.py:231-282,
+    utils/dataloader.py:228-302).  The reference propagates once and then, PER USER, calls
+    `inference_fast`, copies the scores to the host and argsorts them there; here all users' candidates
+    are scored by one `fr_pair_scores` launch and read back once.
+
+    `users [n]`, `cand_ptr [n+1]`, `cand_items [cand_ptr[-1]]` (positives first for each user), `n_pos [n]`
+    are host arrays.  Returns the reference's metric dict."""
+    from . import metrics as M, ops
+    users = np.asarray(users, dtype=np.int64)
+    cand_ptr = np.asarray(cand_ptr, dtype=np.int64)
+    cand_items = np.asarray(cand_items, dtype=np.int64)
+    model.eval()
+    with torch.no_grad():
+        user_all, item_all = model._tables()
+        dev = user_all.device
+        rep = np.repeat(users, np.diff(cand_ptr))
+        scores = ops.pair_scores(user_all, item_all, torch.from_numpy(rep).to(dev), torch.from_numpy(cand_items).to(dev))
+        scores = scores.cpu().numpy()
+    return M.by_user_metrics(scores, cand_ptr, np.asarray(n_pos), neg_num), scores

@@ -63,3 +63,24 @@ def metrics_by_user(doc_list, rel_list):
     gains = [1.0 / np.log2(i + 2) for i, d in enumerate(doc_list) if d in rel]
     idcg = sum(1.0 / np.log2(i + 2) for i in range(min(len(doc_list), len(rel_list))))
     return len(gains) / len(rel_list), float(sum(gains)) / idcg
+
+
+def by_user_metrics(scores: np.ndarray, ptr: np.ndarray, n_pos: np.ndarray, neg_num: int = 500):
+    """The reference's by-user evaluation (FoodRec/common/trainer.py:49-69,231-282) on a flat score
+    array: user `r` owns `scores[ptr[r]:ptr[r+1]]`, its first `n_pos[r]` entries are the positives.
+    Returns {'AUC', 'Recall@10', 'Recall@20', 'NDCG@10', 'NDCG@20'} averaged over users."""
+    disc = 1.0 / np.log2(np.arange(2, 22))
+    rows = np.zeros((len(n_pos), 5))
+    for r in range(len(n_pos)):
+        pred = scores[ptr[r]:ptr[r + 1]]
+        p = int(n_pos[r])
+        order = np.argsort(pred)[::-1]
+        neg = pred[p:]
+        rows[r, 0] = sum(float(np.sum(neg < pred[i])) for i in range(p)) / (p * neg_num)
+        hit = order[:20] < p
+        for j, k in enumerate((10, 20)):
+            h = hit[:k]
+            rows[r, 1 + j] = h.sum() / p
+            rows[r, 3 + j] = (disc[:len(h)] * h).sum() / disc[:min(len(h), p)].sum()
+    m = rows.mean(axis=0)
+    return {"AUC": m[0], "Recall@10": m[1], "Recall@20": m[2], "NDCG@10": m[3], "NDCG@20": m[4]}

@@ -103,3 +103,28 @@ def test_schgn_graphconv_block_vs_oracle(mini_ds):
     close(conv.conv1.bias.grad, b.grad.numpy(), rtol=2e-5)
     out2 = conv(xd, ei.cuda())   # second call reuses the cached plan, like the reference's two calls per batch
     assert torch.equal(out, out2)
+
+
+def test_batched_by_user_evaluation_matches_per_user_oracle(mini_ds):
+    """One launch for all users' (positives + sampled negatives) equals the reference's per-user loop."""
+    from foodrec_b200 import evaluation as E
+    from foodrec_b200.models.lightgcn import LightGCN
+    from oracle import ranking
+    m, g = load(LightGCN, "lightgcn_mini.npz", mini_ds, n_layers=2, reg_weight=0.1)
+    rng = np.random.default_rng(0)
+    users = np.arange(0, 60)
+    cands, n_pos = [], []
+    for u in users:
+        pos = mini_ds.testRatings[u]
+        neg = rng.choice(mini_ds.n_items, size=100, replace=False)
+        cands.append(np.concatenate([pos, neg]))
+        n_pos.append(len(pos))
+    ptr = np.concatenate([[0], np.cumsum([len(c) for c in cands])])
+    res, scores = E.evaluate_by_user(m, users, ptr, np.concatenate(cands), n_pos, neg_num=100)
+    ua, ia = torch.from_numpy(g["fwd/user_all"]), torch.from_numpy(g["fwd/item_all"])
+    per_user = [ranking.inference_scores(ua, ia, torch.full((len(c),), int(u)), torch.from_numpy(c)).numpy()
+                for u, c in zip(users, cands)]
+    close(scores, np.concatenate(per_user))
+    ref = ranking.by_user_eval(per_user, n_pos, neg_num=100)
+    for k in ref:
+        assert abs(res[k] - ref[k]) < 1e-6, (k, res[k], ref[k])

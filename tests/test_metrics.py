@@ -33,3 +33,15 @@ def test_metrics_random_vs_oracle():
         b = ranking.topk_metrics(top, pos, metrics=("recall", "recall2", "ndcg", "precision", "map"))
         assert a == b
         assert np.array_equal(metrics.hit_matrix(top, pos), ranking.hit_matrix(top, pos))
+
+
+def test_by_user_metrics_match_oracle():
+    rng = np.random.default_rng(1)
+    n_pos = rng.integers(1, 6, size=30)
+    lens = n_pos + 50
+    ptr = np.concatenate([[0], np.cumsum(lens)])
+    scores = rng.standard_normal(int(ptr[-1])).astype(np.float32)
+    got = metrics.by_user_metrics(scores, ptr, n_pos, neg_num=50)
+    ref = ranking.by_user_eval([scores[ptr[r]:ptr[r + 1]] for r in range(30)], n_pos.tolist(), neg_num=50)
+    for k in ref:
+        assert abs(got[k] - ref[k]) < 1e-12, (k, got[k], ref[k])

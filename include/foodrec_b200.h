@@ -105,6 +105,12 @@ int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, const int64_
                      const int64_t *reg_cnt_host, const int64_t *reg_pad_host, float reg_den,
                      const float *gnorm, float *const *d_tab_host, void *stream);
 
+/* Row pointers of a CSR from the row indices of a COO (any order; for a row-major-sorted COO -- what the
+ * reference builds, FoodRec/models/cikm_model.py:174-180 -- `col`/`val` are then already in CSR order).
+ * row_ptr: int32[n_rows + 1]; scratch: int32[n_rows]. */
+int fr_csr_from_coo(const int64_t *coo_rows, int64_t nnz, int32_t n_rows, int32_t *row_ptr, int32_t *scratch,
+                    void *stream);
+
 /* Row gather out[r] = tab[idx[r]] and its adjoint d_tab[idx[r]] += g[r] (fp32 atomics).
  * Replaces `E[idx]` indexing at pricai_modelx.py:245-247 and the candidate gathers of
  * `inference_fast` (cikm_model.py:294-302, pricai_modelx.py:278-286). */

@@ -75,3 +75,50 @@ extern "C" int fr_pair_scores(const float *user_tab, const float *item_tab, int3
     pair_scores_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(user_tab, item_tab, d, user, item, n, scores);
     return fr::check_launch("fr_pair_scores");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Row-sorted COO -> CSR row pointers on the device (histogram + single-block scan).  The reference hands
+// its adjacency around as a row-major-sorted COO (`coo_matrix(L)` -> `torch.sparse.FloatTensor`,
+// FoodRec/models/cikm_model.py:174-180) and lets `torch.sparse.mm` rebuild CSR on every call.
+namespace {
+__global__ void coo_count_kernel(const int64_t *__restrict__ rows, long long nnz, int *__restrict__ cnt) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(cnt + rows[i], 1);
+}
+__global__ void scan_rows_kernel(const int *__restrict__ cnt, int n, int *__restrict__ row_ptr) {
+    // one block, chunked inclusive scan; n + 1 outputs
+    __shared__ int carry;
+    __shared__ int buf[1024];
+    if (threadIdx.x == 0) { carry = 0; row_ptr[0] = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        buf[threadIdx.x] = i < n ? cnt[i] : 0;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int v = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (i < n) row_ptr[i + 1] = carry + buf[threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += buf[1023];
+        __syncthreads();
+    }
+}
+}  // namespace
+
+extern "C" int fr_csr_from_coo(const int64_t *coo_rows, int64_t nnz, int32_t n_rows, int32_t *row_ptr, int32_t *scratch,
+                               void *stream) {
+    FR_REQUIRE(nnz >= 0 && n_rows >= 0, "fr_csr_from_coo: nnz=%lld n_rows=%d", (long long)nnz, n_rows);
+    FR_REQUIRE(row_ptr && scratch && (nnz == 0 || coo_rows), "fr_csr_from_coo: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(scratch, 0, sizeof(int32_t) * (size_t)std::max(n_rows, 1), st);
+    if (nnz > 0) {
+        coo_count_kernel<<<grid1d(nnz, 256), 256, 0, st>>>(coo_rows, nnz, scratch);
+        if (int rc = fr::check_launch("fr_csr_from_coo/count")) return rc;
+    }
+    scan_rows_kernel<<<1, 1024, 0, st>>>(scratch, n_rows, row_ptr);
+    return fr::check_launch("fr_csr_from_coo/scan");
+}

@@ -131,3 +131,23 @@ def gcn_normalised(src, dst, n_nodes: int, device) -> PropGraph:
     bwd = PropGraph(*build(src, dst), n_nodes, device)
     fwd.T, bwd.T = bwd, fwd
     return fwd
+
+
+def from_torch_sparse(S: torch.Tensor, symmetric: bool = True) -> PropGraph:
+    """PropGraph from a reference-built adjacency: a row-major-sorted, duplicate-free
+    `torch.sparse` COO on the device (what `get_norm_adj_mat` returns after `.to(device)`,
+    FoodRec/models/cikm_model.py:74,174-180).  Row pointers are computed on the device
+    (`fr_csr_from_coo`); values and column order are taken as they are."""
+    idx, val = S._indices(), S._values()
+    if idx.device.type != "cuda":
+        raise _lib.FoodRecError("from_torch_sparse needs a CUDA sparse tensor")
+    n = int(S.shape[0])
+    rows = idx[0].contiguous()
+    if rows.numel() > 1 and bool((rows[1:] < rows[:-1]).any()):
+        raise _lib.FoodRecError("COO rows are not sorted; coalesce() first")
+    row_ptr = torch.empty(n + 1, dtype=torch.int32, device=idx.device)
+    scratch = torch.empty(max(n, 1), dtype=torch.int32, device=idx.device)
+    _lib.check(_lib.lib.fr_csr_from_coo(rows.data_ptr(), rows.numel(), n, row_ptr.data_ptr(), scratch.data_ptr(),
+                                        _lib.stream_ptr()), "fr_csr_from_coo")
+    return PropGraph(row_ptr.cpu().numpy(), idx[1].to(torch.int32).cpu().numpy(), val.float().cpu().numpy(), int(S.shape[1]),
+                     idx.device, transpose="self" if symmetric else None)

@@ -128,3 +128,35 @@ def test_batched_by_user_evaluation_matches_per_user_oracle(mini_ds):
     ref = ranking.by_user_eval(per_user, n_pos, neg_num=100)
     for k in ref:
         assert abs(res[k] - ref[k]) < 1e-6, (k, res[k], ref[k])
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_model_level_full_sort_evaluation_metrics(masked):
+    """`Trainer.evaluate` semantics at model level (C1): propagate, rank every user against all items on the
+    tensor cores, Recall/NDCG/Precision/MAP @5/10/20/50 equal to the fp32 oracle ranking to 4 decimals."""
+    from foodrec_b200 import evaluation as E
+    from foodrec_b200.models.lightgcn import LightGCN
+    from foodrec_b200.synth import make_dataset
+    from oracle import adjacency, propagation, ranking
+    ds = make_dataset("C1")
+    torch.manual_seed(999)
+    m = LightGCN(Cfg({**BASE, "n_layers": 2, "reg_weight": 0.1}), ds)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to("cuda")
+    users = np.arange(ds.n_users)
+    pos = [ds.testRatings[u] for u in users]
+    hist = E.HistoryCSR(ds.train_coo_matrix, ds.n_users, "cuda") if masked else None
+    res, top = E.evaluate_full_sort(m, users, pos, hist=hist)
+    # oracle: CPU propagation + dense fp32 scores + torch.topk (+ mask), reference metric definitions
+    S = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    ego = sd["image_embedding.weight"] @ sd["image_trs.weight"].t() + sd["image_trs.bias"]
+    ua, ia = propagation.lightgcn_forward(S, sd["user_embedding.weight"], ego, ds.n_users, ds.n_items, 2)
+    if masked:
+        _, ref_top = ranking.full_sort_topk(ua, ia, torch.arange(ds.n_users), 50, hist.ptr_host, hist.idx_host.astype(np.int64))
+    else:
+        _, ref_top = ranking.full_sort_topk(ua, ia, torch.arange(ds.n_users), 50)
+    ref = ranking.topk_metrics(ref_top.numpy(), pos)
+    assert res == ref, {k: (res[k], ref[k]) for k in ref if res[k] != ref[k]}
+    # index-level: differences only where the fp32 scores tie (GPU vs CPU propagation differ by ~1e-7)
+    diff = top != ref_top.numpy()
+    assert diff.mean() < 2e-3

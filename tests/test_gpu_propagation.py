@@ -129,3 +129,18 @@ def test_c1_scale_forward_vs_oracle():
     torch.manual_seed(0)
     ego = torch.randn(ds.n_users + ds.n_items, 64) * 0.1
     close(ops.propagate_mean(g, ego.cuda(), 2), propagation.layer_mean_propagate(S, ego, 2))
+
+
+def test_propgraph_from_reference_style_sparse_tensor(mini_ds):
+    """A reference-built adjacency (row-sorted torch COO on the device) becomes a plan through the
+    device-side COO -> CSR kernel and propagates like `torch.sparse.mm` on it."""
+    from foodrec_b200 import graph as G, ops
+    from oracle import adjacency
+    ds = mini_ds
+    S = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    g = G.from_torch_sparse(S.cuda())
+    g0 = G.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items, "cuda")
+    assert np.array_equal(g.row_ptr_host, g0.row_ptr_host)
+    assert torch.equal(g.col, g0.col) and torch.equal(g.val, g0.val)
+    X = torch.randn(S.shape[0], 64)
+    close(ops.spmm(g, X.cuda()), torch.sparse.mm(S, X))

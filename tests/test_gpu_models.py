@@ -141,7 +141,7 @@ def test_model_level_full_sort_evaluation_metrics(masked):
     ds = make_dataset("C1")
     torch.manual_seed(999)
     m = LightGCN(Cfg({**BASE, "n_layers": 2, "reg_weight": 0.1}), ds)
-    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
     m = m.to("cuda")
     users = np.arange(ds.n_users)
     pos = [ds.testRatings[u] for u in users]

@@ -47,23 +47,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
+    // suspend-time hint: a waiting thread may sleep up to ~1 us in hardware and is woken by the phase flip,
+    // instead of burning issue slots that the epilogue warps on the same scheduler need
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must fault the launch, never hang the GPU.
+// Bounded wait: a protocol bug must fault the launch, never hang the GPU.  The clock is consulted only
+// every 256 failed polls (each poll already sleeps in hardware), so the common path is poll + branch.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("foodrec_b200 gemm_topk: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
+    long long t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try(bar, parity)) return;
+        if ((spins & 255u) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) {
+                printf("foodrec_b200 gemm_topk: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+                __trap();
+            }
         }
     }
 }

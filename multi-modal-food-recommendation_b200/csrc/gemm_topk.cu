@@ -47,14 +47,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
-    // suspend-time hint: a waiting thread may sleep up to ~1 us in hardware and is woken by the phase flip,
-    // instead of burning issue slots that the epilogue warps on the same scheduler need
+    // (an explicit suspend-time hint of 1 us was measured: 40.0 -> 47.6 ms on 200k x 500k; the default wins)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }

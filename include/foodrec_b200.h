@@ -72,6 +72,15 @@ int fr_spmm_csr_f32(const int32_t *seg, int64_t n_seg, const int32_t *long_rows,
                     float alpha, float beta, const float *bias, int32_t act, float *Y, float *partial,
                     int32_t *counters, void *stream);
 
+/* Same, with two-segment operands: rows [0, x_split) of X come from X0 and rows >= x_split from X1 (row
+ * r of the logical table = X1[r - x_split]); likewise Z0 / Z1 / z_split.  X1 == NULL / Z1 == NULL: single
+ * table.  Consumes the reference's `torch.cat((user_w, item_emb))` / `cat((item_w, side_w))` ego tables
+ * (cikm_model.py:184,195; pricai_modelx.py:180,192-194,206-208,220) without materialising them. */
+int fr_spmm_csr_f32_split(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                          const int32_t *col_idx, const float *val, int32_t d, const float *X0, const float *X1,
+                          int32_t x_split, const float *Z0, const float *Z1, int32_t z_split, float alpha, float beta,
+                          const float *bias, int32_t act, float *Y, float *partial, int32_t *counters, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused ranking loss on gathered rows: BPR + embedding regulariser, forward and backward.
  * Replaces the gathers, `torch.mul(..).sum(1)`, `BPRLoss` and `EmbLoss` at
@@ -111,6 +120,13 @@ int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, const int64_
 int fr_csr_from_coo(const int64_t *coo_rows, int64_t nnz, int32_t n_rows, int32_t *row_ptr, int32_t *scratch,
                     void *stream);
 
+/* out[r] = sum_v tab_v[r], r < rows (`item_emb = ingre[:I] + image[:I] + text[:I]`, pricai_modelx.py:219), and
+ * the adjoint d_tab_v[r] = (r < rows ? g[r] : 0) over each table's full height rows_total[v] (slice gradient +
+ * zero fill of up to four tables in one launch). */
+int fr_sum_rows(const float *const *tab_host, int32_t n_tabs, int32_t d, int64_t rows, float *out, void *stream);
+int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *const *d_tab_host, const int64_t *rows_total_host,
+                   int32_t n_tabs, void *stream);
+
 /* Row gather out[r] = tab[idx[r]] and its adjoint d_tab[idx[r]] += g[r] (fp32 atomics).
  * Replaces `E[idx]` indexing at pricai_modelx.py:245-247 and the candidate gathers of
  * `inference_fast` (cikm_model.py:294-302, pricai_modelx.py:278-286). */
@@ -125,7 +141,8 @@ int fr_pair_scores(const float *user_tab, const float *item_tab, int32_t d, cons
  * Replaces `PRICAI_ModelX.correlation_distance` (FoodRec/models/pricai_modelx.py:409-437) and the
  * three calls + row gathers at :245-247,263.  V <= 3 views are rows `idx[0..n)` of `tab_host[v]`
  * ([rows_v, d] fp32, d in {32, 64}); P <= 3 pairs (a_p, b_p) index the views.
- *   out[p]  = dcov(a,b) / sqrt(max(dcov(a,a) dcov(b,b), 0) + 1e-10),
+ *   out[p]  = scale * dcov(a,b) / sqrt(max(dcov(a,a) dcov(b,b), 0) + 1e-10),  out[P] = sum_p out[p]
+ *             (scale = CLUSSL's `loss_cl`, so `loss_cl * (dcor + dcor + dcor)` costs no extra launch),
  *   dcov(x,y) = sqrt(max(sum(A_x o A_y) / n^2, 0) + 1e-8), A = double-centred
  *   sqrt(max(r_i - 2 x_i.x_j + r_j, 0) + 1e-8).
  * Caller-provided state kept for the backward: Dm [V, n, n], rowmean [V, n], dfds [3 P], gm [V];
@@ -134,8 +151,8 @@ int fr_pair_scores(const float *user_tab, const float *item_tab, int32_t d, cons
  * += sum_p g_out[p] * d out[p] / d tab_v  via fp32 atomics. */
 int64_t fr_dcor_ws_floats(int32_t n);
 int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
-                const int32_t *pairs_host, int32_t P, float *Dm, float *rowmean, float *out, float *dfds,
-                float *gm, float *ws, void *stream);
+                const int32_t *pairs_host, int32_t P, float scale, float *Dm, float *rowmean, float *out /* [P + 1] */,
+                float *dfds, float *gm, float *ws, void *stream);
 int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
                 const int32_t *pairs_host, int32_t P, const float *Dm, const float *rowmean,
                 const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host, void *stream);

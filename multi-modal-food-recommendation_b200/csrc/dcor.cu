@@ -128,7 +128,7 @@ __global__ void dcor_rowmean_kernel(const float *__restrict__ rowpart, int n, in
 __global__ void __launch_bounds__(kThreads)
 dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const float *__restrict__ rowmean,
                 float *__restrict__ out, float *__restrict__ dfds, float *__restrict__ gm_out,
-                float *__restrict__ ws) {
+                float *__restrict__ ws, float scale) {
     __shared__ float red[kThreads / 32];
     __shared__ float gm[kMaxV];
     __shared__ float fin[6];
@@ -183,6 +183,7 @@ dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const floa
             if (a > b) { const int t = a; a = b; b = t; }
             return fin[a * 3 + b - (a * (a + 1)) / 2];
         };
+        float total = 0.f;
         for (int p = 0; p < pr.P; ++p) {
             const int a = pr.a[p], b = pr.b[p];
             const float sab = S(a, b), saa = S(a, a), sbb = S(b, b);
@@ -190,12 +191,14 @@ dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const floa
             const float caa = sqrtf(fmaxf(saa, 0.f) + 1e-8f);
             const float cbb = sqrtf(fmaxf(sbb, 0.f) + 1e-8f);
             const float q = sqrtf(fmaxf(caa * cbb, 0.f) + 1e-10f);
-            out[p] = cab / q;
+            out[p] = scale * (cab / q);
+            total += out[p];
             const float dq = -cab / (2.f * q * q * q);  // d f / d (caa*cbb)
-            dfds[p * 3 + 0] = sab > 0.f ? 1.f / (2.f * cab * q) : 0.f;
-            dfds[p * 3 + 1] = saa > 0.f ? dq * cbb / (2.f * caa) : 0.f;
-            dfds[p * 3 + 2] = sbb > 0.f ? dq * caa / (2.f * cbb) : 0.f;
+            dfds[p * 3 + 0] = sab > 0.f ? scale / (2.f * cab * q) : 0.f;
+            dfds[p * 3 + 1] = saa > 0.f ? scale * dq * cbb / (2.f * caa) : 0.f;
+            dfds[p * 3 + 2] = sbb > 0.f ? scale * dq * caa / (2.f * cbb) : 0.f;
         }
+        out[pr.P] = total;      // sum of the (scaled) terms, the value CLUSSL's loss uses
         for (int v = 0; v < V; ++v) gm_out[v] = gm[v];
         *reinterpret_cast<int *>(ws) = 0;
     }
@@ -330,8 +333,8 @@ extern "C" int64_t fr_dcor_ws_floats(int32_t n) {
 }
 
 extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
-                           const int32_t *pairs_host, int32_t P, float *Dm, float *rowmean, float *out, float *dfds,
-                           float *gm, float *ws, void *stream) {
+                           const int32_t *pairs_host, int32_t P, float scale, float *Dm, float *rowmean, float *out,
+                           float *dfds, float *gm, float *ws, void *stream) {
     FR_REQUIRE(idx && Dm && rowmean && out && dfds && gm && ws && n > 0, "fr_dcor_fwd: bad argument");
     Views vw;
     Pairs pr;
@@ -353,7 +356,7 @@ extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, c
     dcor_rowmean_kernel<<<dim3((n + 255) / 256, V), 256, 0, st>>>(rowpart, n, n_tiles, V, rowmean);
     if (int rc = fr::check_launch("fr_dcor_fwd/rowmean")) return rc;
     fr::LaunchTimer _lt2("dcor_dot_kernel", st);
-    dcor_dot_kernel<<<(n + kRB2 - 1) / kRB2, kThreads, 0, st>>>(V, pr, n, Dm, rowmean, out, dfds, gm, ws);
+    dcor_dot_kernel<<<(n + kRB2 - 1) / kRB2, kThreads, 0, st>>>(V, pr, n, Dm, rowmean, out, dfds, gm, ws, scale);
     return fr::check_launch("fr_dcor_fwd/dot");
 }
 

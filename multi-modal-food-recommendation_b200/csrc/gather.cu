@@ -122,3 +122,66 @@ extern "C" int fr_csr_from_coo(const int64_t *coo_rows, int64_t nnz, int32_t n_r
     scan_rows_kernel<<<1, 1024, 0, st>>>(scratch, n_rows, row_ptr);
     return fr::check_launch("fr_csr_from_coo/scan");
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// out[r] = sum_v tab_v[r] for r < rows (CLUSSL: item_emb = ingre[:I] + image[:I] + text[:I],
+// FoodRec/models/pricai_modelx.py:219) and its adjoint: d_tab_v[r] = r < rows ? g[r] : 0 over each table's
+// full height, i.e. the zero-fill and the slice-gradient of all three tables in one launch.
+namespace {
+struct Tabs4 {
+    const float *in[4];
+    float *out[4];
+    long long rows_total[4];
+    int n;
+};
+__global__ void sum_rows_kernel(Tabs4 t, long long n4, float *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = fr::ldg_f4(t.in[0] + 4 * i);
+        for (int v = 1; v < t.n; ++v) fr::add4(a, fr::ldg_f4(t.in[v] + 4 * i));
+        reinterpret_cast<float4 *>(out)[i] = a;
+    }
+}
+__global__ void spread_rows_kernel(Tabs4 t, long long n4_src, const float *__restrict__ g) {
+    const int v = blockIdx.y;
+    float4 *dst = reinterpret_cast<float4 *>(t.out[v]);
+    if (dst == nullptr) return;
+    const long long tot4 = t.rows_total[v];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot4; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = i < n4_src ? fr::ldg_f4(g + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+}  // namespace
+
+extern "C" int fr_sum_rows(const float *const *tab_host, int32_t n_tabs, int32_t d, int64_t rows, float *out, void *stream) {
+    FR_REQUIRE(n_tabs >= 1 && n_tabs <= 4 && d > 0 && d % 4 == 0 && rows >= 0 && tab_host && out, "fr_sum_rows: bad argument");
+    if (rows == 0) return FR_OK;
+    Tabs4 t{};
+    t.n = n_tabs;
+    for (int v = 0; v < n_tabs; ++v) {
+        FR_REQUIRE(tab_host[v], "fr_sum_rows: null table %d", v);
+        t.in[v] = tab_host[v];
+    }
+    const long long n4 = rows * (d / 4);
+    fr::LaunchTimer _lt("sum_rows_kernel", (cudaStream_t)stream);
+    sum_rows_kernel<<<grid1d(n4, 256), 256, 0, (cudaStream_t)stream>>>(t, n4, out);
+    return fr::check_launch("fr_sum_rows");
+}
+
+extern "C" int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *const *d_tab_host, const int64_t *rows_total_host,
+                              int32_t n_tabs, void *stream) {
+    FR_REQUIRE(n_tabs >= 1 && n_tabs <= 4 && d > 0 && d % 4 == 0 && rows >= 0 && g && d_tab_host && rows_total_host,
+               "fr_spread_rows: bad argument");
+    Tabs4 t{};
+    t.n = n_tabs;
+    long long mx = 0;
+    for (int v = 0; v < n_tabs; ++v) {
+        FR_REQUIRE(rows_total_host[v] >= rows, "fr_spread_rows: table %d shorter than the source", v);
+        t.out[v] = d_tab_host[v];
+        t.rows_total[v] = rows_total_host[v] * (d / 4);
+        mx = std::max(mx, t.rows_total[v]);
+    }
+    if (mx == 0) return FR_OK;
+    fr::LaunchTimer _lt("spread_rows_kernel", (cudaStream_t)stream);
+    spread_rows_kernel<<<dim3(grid1d(mx, 256), n_tabs), 256, 0, (cudaStream_t)stream>>>(t, rows * (d / 4), g);
+    return fr::check_launch("fr_spread_rows");
+}

@@ -19,6 +19,17 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
+// Optional two-segment operands: rows [0, split) come from the primary pointer, rows >= split from a second
+// table (`*_adj` = second pointer - split * D, so both are indexed by the global row).  This is how the
+// reference's `torch.cat((user_w, item_emb))` / `cat((item_w, side_w))` ego tables are consumed without
+// materialising the concatenation.  split = INT_MAX: single table.
+struct Split {
+    const float *X1_adj;
+    int x_split;
+    const float *Z1_adj;
+    int z_split;
+};
+
 template <int D>
 struct Shape {
     static constexpr int LPR = D / 4;    // lanes per embedding row (one float4 each)
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
                   const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
                   const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,
-                  float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters) {
+                  float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters, Split sp) {
     constexpr int G = 32 / LPR, VPL = D / (4 * LPR);
     static_assert(VPL >= 1 && LPR % U == 0, "bad group shape");
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -321,6 +332,7 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
     const int *__restrict__ cp = col + s.y;
     const float *__restrict__ vp = val + s.y;
     const float *__restrict__ Xo = X + lg * 4;           // slice t of this lane starts at column 4 (lg + LPR t)
+    const float *__restrict__ X1o = sp.X1_adj + lg * 4;
 
     float4 acc[VPL];
 #pragma unroll
@@ -342,7 +354,7 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
                 const int e = j + u;
                 const int cj = __shfl_sync(0xffffffffu, c, e, LPR);
                 vv[u] = __shfl_sync(0xffffffffu, v, e, LPR);
-                const float *xr = Xo + (size_t)cj * D;
+                const float *xr = (cj < sp.x_split ? Xo : X1o) + (size_t)cj * D;
                 if (e < cnt) {
 #pragma unroll
                     for (int t = 0; t < VPL; ++t) x[u][t] = fr::ldg_f4(xr + 4 * LPR * t);
@@ -361,7 +373,9 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
     if (s.w == -2) return;
     if (s.w < 0) {
 #pragma unroll
-        for (int t = 0; t < VPL; ++t) epilogue_store<D, ACT>(acc[t], s.x, 4 * (lg + LPR * t), Z, alpha, beta, bias, Y);
+        for (int t = 0; t < VPL; ++t)
+            epilogue_store<D, ACT>(acc[t], s.x, 4 * (lg + LPR * t), (Z != nullptr && s.x >= sp.z_split) ? sp.Z1_adj : Z, alpha,
+                                   beta, bias, Y);
         return;
     }
     // ---- long row: publish this segment's partial; the last segment to arrive folds all in fixed order
@@ -391,7 +405,8 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
             for (int u = 0; u < 8; ++u) fr::add4(tot, p8[u]);
         }
         for (; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(pp + (size_t)k * D));
-        epilogue_store<D, ACT>(tot, lr.w, 4 * (lg + LPR * t), Z, alpha, beta, bias, Y);
+        epilogue_store<D, ACT>(tot, lr.w, 4 * (lg + LPR * t), (Z != nullptr && lr.w >= sp.z_split) ? sp.Z1_adj : Z, alpha, beta,
+                               bias, Y);
     }
     if (lg == 0) counters[s.w] = 0;
 }
@@ -399,7 +414,7 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
 template <int D, int LPR, int U, int ACT>
 int launch_group_shape(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val,
                        const float *X, const float *Z, float alpha, float beta, const float *bias, float *Y,
-                       float *partial, int *counters, cudaStream_t st) {
+                       float *partial, int *counters, cudaStream_t st, Split sp) {
     constexpr int G = 32 / LPR;
     const long long warps = (n_seg + G - 1) / G;
     const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -409,20 +424,20 @@ int launch_group_shape(const int4 *seg, int64_t n_seg, const int4 *lrows, const 
     }
     fr::LaunchTimer _lt("spmm_group_kernel", st);
     spmm_group_kernel<D, LPR, U, ACT><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-        seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters);
+        seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
     return fr::check_launch("fr_spmm_csr_f32(group)");
 }
 
 template <int D, int ACT>
 int launch_group(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val, const float *X,
                  const float *Z, float alpha, float beta, const float *bias, float *Y, float *partial, int *counters,
-                 cudaStream_t st) {
+                 cudaStream_t st, Split sp) {
     static int shape = -1;                               // tuning knob: FR_SPMM_SHAPE = lanes-per-row * 10 + unroll
     if (shape < 0) {
         const char *e = getenv("FR_SPMM_SHAPE");
         shape = e ? atoi(e) : 84;
     }
-#define FR_GO(L, UU) return launch_group_shape<D, L, UU, ACT>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st)
+#define FR_GO(L, UU) return launch_group_shape<D, L, UU, ACT>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st, sp)
     if constexpr (D >= 64) {
         if (shape == 42) FR_GO(4, 2);
         if (shape == 44) FR_GO(4, 4);
@@ -468,15 +483,19 @@ int launch_bulk(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *co
 template <int D>
 int launch(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, const float *val, const float *X,
            const float *Z, float alpha, float beta, const float *bias, int act, float *Y, float *partial,
-           int *counters, cudaStream_t st) {
+           int *counters, cudaStream_t st, Split sp) {
     const long long blocks = (n_seg + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > 0x7fffffffLL) {
         fr::set_error("fr_spmm_csr_f32: too many segments (%lld)", (long long)n_seg);
         return FR_EUNSUPPORTED;
     }
     if (spmm_impl() == 2) {
-        if (act == 0) return launch_group<D, 0>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st);
-        return launch_group<D, 1>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st);
+        if (act == 0) return launch_group<D, 0>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st, sp);
+        return launch_group<D, 1>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st, sp);
+    }
+    if (sp.x_split != 0x7fffffff || sp.z_split != 0x7fffffff) {
+        fr::set_error("fr_spmm_csr_f32_split: two-segment operands need the default (group) kernel");
+        return FR_EUNSUPPORTED;
     }
     if (spmm_impl() == 1) {
         if (act == 0) return launch_bulk<D, 0>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st);
@@ -575,28 +594,44 @@ extern "C" int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, in
     return FR_OK;
 }
 
-extern "C" int fr_spmm_csr_f32(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
-                               const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z,
-                               float alpha, float beta, const float *bias, int32_t act, float *Y, float *partial,
-                               int32_t *counters, void *stream) {
+extern "C" int fr_spmm_csr_f32_split(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                                     const int32_t *col_idx, const float *val, int32_t d, const float *X0, const float *X1,
+                                     int32_t x_split, const float *Z0, const float *Z1, int32_t z_split, float alpha,
+                                     float beta, const float *bias, int32_t act, float *Y, float *partial,
+                                     int32_t *counters, void *stream) {
     FR_REQUIRE(n_seg >= 0 && n_long >= 0, "fr_spmm_csr_f32: negative extent");
     if (n_seg == 0) return FR_OK;
-    FR_REQUIRE(seg && X && Y, "fr_spmm_csr_f32: null seg/X/Y");
+    FR_REQUIRE(seg && X0 && Y, "fr_spmm_csr_f32: null seg/X/Y");
     FR_REQUIRE(n_long == 0 || (long_rows && partial && counters), "fr_spmm_csr_f32: long rows need workspace");
     FR_REQUIRE(act == 0 || act == 1, "fr_spmm_csr_f32: act must be 0 or 1");
-    FR_REQUIRE((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)Z | (uintptr_t)bias | (uintptr_t)partial |
-                 (uintptr_t)seg | (uintptr_t)long_rows) & 15) == 0,
+    FR_REQUIRE((((uintptr_t)X0 | (uintptr_t)X1 | (uintptr_t)Y | (uintptr_t)Z0 | (uintptr_t)Z1 | (uintptr_t)bias |
+                 (uintptr_t)partial | (uintptr_t)seg | (uintptr_t)long_rows) & 15) == 0,
                "fr_spmm_csr_f32: pointers must be 16-byte aligned");
-    FR_REQUIRE(X != Y, "fr_spmm_csr_f32: in-place propagation is not supported");
+    FR_REQUIRE(X0 != Y && X1 != Y, "fr_spmm_csr_f32: in-place propagation is not supported");
+    FR_REQUIRE(x_split >= 0 && z_split >= 0 && (X1 != nullptr || x_split == 0) && (Z1 == nullptr || Z0 != nullptr),
+               "fr_spmm_csr_f32_split: bad split arguments");
+    Split sp;
+    sp.x_split = X1 ? x_split : 0x7fffffff;
+    sp.X1_adj = X1 ? X1 - (size_t)x_split * d : X0;
+    sp.z_split = Z1 ? z_split : 0x7fffffff;
+    sp.Z1_adj = Z1 ? Z1 - (size_t)z_split * d : Z0;
     cudaStream_t st = (cudaStream_t)stream;
     const int4 *sg = reinterpret_cast<const int4 *>(seg);
     const int4 *lr = reinterpret_cast<const int4 *>(long_rows);
     switch (d) {
-        case 32: return launch<32>(sg, n_seg, lr, col_idx, val, X, Z, alpha, beta, bias, act, Y, partial, counters, st);
-        case 64: return launch<64>(sg, n_seg, lr, col_idx, val, X, Z, alpha, beta, bias, act, Y, partial, counters, st);
-        case 128: return launch<128>(sg, n_seg, lr, col_idx, val, X, Z, alpha, beta, bias, act, Y, partial, counters, st);
+        case 32: return launch<32>(sg, n_seg, lr, col_idx, val, X0, Z0, alpha, beta, bias, act, Y, partial, counters, st, sp);
+        case 64: return launch<64>(sg, n_seg, lr, col_idx, val, X0, Z0, alpha, beta, bias, act, Y, partial, counters, st, sp);
+        case 128: return launch<128>(sg, n_seg, lr, col_idx, val, X0, Z0, alpha, beta, bias, act, Y, partial, counters, st, sp);
         default:
             fr::set_error("fr_spmm_csr_f32: d=%d unsupported (32, 64, 128)", d);
             return FR_EUNSUPPORTED;
     }
+}
+
+extern "C" int fr_spmm_csr_f32(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                               const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z,
+                               float alpha, float beta, const float *bias, int32_t act, float *Y, float *partial,
+                               int32_t *counters, void *stream) {
+    return fr_spmm_csr_f32_split(seg, n_seg, long_rows, n_long, col_idx, val, d, X, nullptr, 0, Z, nullptr, 0, alpha, beta,
+                                 bias, act, Y, partial, counters, stream);
 }

@@ -112,10 +112,8 @@ class CIKM_Model(DotProductRecommender):
 
     # ------------------------------------------------------------------ propagation
     def _propagate_all(self):
-        ir = ops.propagate_mean(self.g_ri, torch.cat((self.item_embedding.weight, self.ingre_embedding.weight[:-1]), 0),
-                                self.n_layers)
-        all_emb = ops.propagate_mean(self.g_ui, torch.cat((self.user_embedding.weight, ir[:self.n_items]), 0),
-                                     self.ui_layers)
+        ir = ops.propagate_mean(self.g_ri, self.item_embedding.weight, self.n_layers, bottom=self.ingre_embedding.weight[:-1])
+        all_emb = ops.propagate_mean(self.g_ui, self.user_embedding.weight, self.ui_layers, bottom=ir[:self.n_items])
         return all_emb, ir
 
     def forward(self):

@@ -38,7 +38,8 @@ class LightGCN(DotProductRecommender):
         return torch.cat([self.user_embedding.weight, self.image_trs(self.image_embedding.weight)], dim=0)
 
     def _propagate_all(self):
-        return (ops.propagate_mean(self.g_ui, self.get_ego_embeddings(), self.n_layers),)
+        return (ops.propagate_mean(self.g_ui, self.user_embedding.weight, self.n_layers,
+                                   bottom=self.image_trs(self.image_embedding.weight)),)
 
     def forward(self):
         all_emb = self._propagate_all()[0]

@@ -96,30 +96,27 @@ class PRICAI_ModelX(DotProductRecommender):
             s1 = s2 = cur
         s1.wait_stream(cur)
         s2.wait_stream(cur)
-        ing = ops.propagate_mean(self.g_ingre, torch.cat((item_w, self.ingre_embedding.weight[:-1]), 0),
-                                 self.n_ri_layers)
+        ing = ops.propagate_mean(self.g_ingre, item_w, self.n_ri_layers, bottom=self.ingre_embedding.weight[:-1])
         with torch.cuda.stream(s1):
             image_proto = self.image_prototype_embedding.weight
             if self.v_center is not None:
                 image_proto = self.image_trs(image_proto)
-            img = ops.propagate_mean(self.g_image, torch.cat((item_w, image_proto), 0), self.n_ri_layers)
+            img = ops.propagate_mean(self.g_image, item_w, self.n_ri_layers, bottom=image_proto)
         with torch.cuda.stream(s2):
             text_proto = self.text_prototype_embedding.weight
             if self.t_center is not None:
                 text_proto = self.text_trs(text_proto)
-            txt = ops.propagate_mean(self.g_text, torch.cat((item_w, text_proto), 0), self.n_ri_layers)
+            txt = ops.propagate_mean(self.g_text, item_w, self.n_ri_layers, bottom=text_proto)
         cur.wait_stream(s1)
         cur.wait_stream(s2)
         for t in (img, txt):
             t.record_stream(cur)
         side = None
-        if side_fn is not None:   # work that only needs the item-side views runs beside the user-item propagation
-            s1.wait_stream(cur)
-            with torch.cuda.stream(s1):
-                side = side_fn(img, txt, ing)
-        item_emb = ing[:I] + img[:I] + txt[:I]
-        all_emb = ops.propagate_mean(self.g_ui, torch.cat((self.user_embedding.weight, item_emb), 0),
-                                     self.n_ui_layers)
+        if side_fn is not None:   # training: item_emb and the contrastive total come from one fused op
+            item_emb, side = side_fn(img, txt, ing)
+        else:
+            item_emb = ing[:I] + img[:I] + txt[:I]
+        all_emb = ops.propagate_mean(self.g_ui, self.user_embedding.weight, self.n_ui_layers, bottom=item_emb)
         if side_fn is not None:
             return all_emb, (img, txt, ing), side
         return all_emb, (img, txt, ing)
@@ -133,21 +130,17 @@ class PRICAI_ModelX(DotProductRecommender):
     def calculate_loss(self, batch_data):
         user, pos_item, neg_item = batch_data["u_id"], batch_data["pos_i_id"], batch_data["neg_i_id"]
         all_item = torch.cat([pos_item, neg_item], dim=0)
-        # views are rows `all_item` (< n_items) of the propagated [I + C, d] tables, gathered in-kernel:
-        # dcor(image, text) + dcor(image, ingre) + dcor(ingre, text).  Latency-bound, so it runs on a side
-        # stream beside the user-item propagation and the ranking loss.
-        def contrastive(img, txt, ing):
-            return ops.dcor_terms([img, txt, ing], all_item, [(0, 1), (0, 2), (2, 1)]).sum().reshape(1)
-        all_emb, (img, txt, ing), cl_loss = self._propagate_all(side_fn=contrastive)
+        # The views are rows `all_item` (< n_items) of the propagated [I + C, d] tables, gathered in-kernel:
+        # loss_cl * (dcor(image, text) + dcor(image, ingre) + dcor(ingre, text)), fused with
+        # item_emb = ingre[:I] + image[:I] + text[:I]; `loss_cl` and `reg_weight` are folded into the kernels.
+        def views(img, txt, ing):
+            return ops.item_views([img, txt, ing], all_item, [(0, 1), (0, 2), (2, 1)], self.loss_cl, self.n_items)
+        all_emb, _, cl_loss = self._propagate_all(side_fn=views)
         uw, iw = self.user_embedding.weight, self.item_embedding.weight
         mf_loss_g, reg = ops.rank_loss(all_emb, self.n_users, user, pos_item, neg_item,
                                        [(uw, user), (iw, pos_item), (iw, neg_item)],
-                                       reg_den=float(neg_item.shape[0]), gamma=self.mf_loss.gamma)
-        cur = torch.cuda.current_stream()
-        if getattr(self, "fork_streams", True):
-            cur.wait_stream(self._side_streams()[0])
-            cl_loss.record_stream(cur)
-        return mf_loss_g, self.loss_cl * cl_loss, (self.reg_weight * reg).reshape(1)
+                                       reg_den=float(neg_item.shape[0]) / self.reg_weight, gamma=self.mf_loss.gamma)
+        return mf_loss_g, cl_loss, reg.reshape(1)
 
     def CL_loss(self, hidden, hidden_norm=True, temperature=0.5):
         return ops.info_nce(hidden, temperature=temperature, hidden_norm=hidden_norm)

@@ -33,27 +33,31 @@ def _idx(t: torch.Tensor, name: str) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------ propagation
 def spmm(graph: PropGraph, X: torch.Tensor, Z: torch.Tensor | None = None, alpha: float = 1.0, beta: float = 0.0,
-         bias: torch.Tensor | None = None, act: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
-    """`out = act(alpha * S @ X + beta * Z + bias)`; no autograd."""
+         bias: torch.Tensor | None = None, act: int = 0, out: torch.Tensor | None = None,
+         X1: torch.Tensor | None = None, Z1: torch.Tensor | None = None) -> torch.Tensor:
+    """`out = act(alpha * S @ [X; X1] + beta * [Z; Z1] + bias)`; no autograd.  `X1` / `Z1` are optional
+    second segments (rows stacked under `X` / `Z`), read in place instead of concatenating."""
     _chk_f32(X, "X")
-    if X.shape[0] != graph.n_cols:
-        raise _lib.FoodRecError(f"X has {X.shape[0]} rows, graph has {graph.n_cols} columns")
+    rows = X.shape[0] + (X1.shape[0] if X1 is not None else 0)
+    if rows != graph.n_cols:
+        raise _lib.FoodRecError(f"X has {rows} rows, graph has {graph.n_cols} columns")
     d = X.shape[1]
     if out is None:
         out = torch.empty((graph.n_rows, d), dtype=torch.float32, device=X.device)
-    if Z is not None:
-        _chk_f32(Z, "Z")
-    if bias is not None:
-        _chk_f32(bias, "bias")
+    for t, name in ((X1, "X1"), (Z, "Z"), (Z1, "Z1"), (bias, "bias")):
+        if t is not None:
+            _chk_f32(t, name)
+    if Z is not None and Z.shape[0] + (Z1.shape[0] if Z1 is not None else 0) != graph.n_rows:
+        raise _lib.FoodRecError("Z does not have one row per graph row")
     prof = PROFILE
     if prof is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
-    _lib.check(_L.fr_spmm_csr_f32(
+    _lib.check(_L.fr_spmm_csr_f32_split(
         graph.seg.data_ptr(), graph.n_seg, graph.long_rows.data_ptr(), graph.n_long, graph.col.data_ptr(),
-        graph.val.data_ptr(), d, X.data_ptr(), _lib.ptr(Z), float(alpha), float(beta), _lib.ptr(bias), int(act),
-        out.data_ptr(), graph.partial(d).data_ptr(), graph.counters.data_ptr(), _lib.stream_ptr()),
-        "fr_spmm_csr_f32")
+        graph.val.data_ptr(), d, X.data_ptr(), _lib.ptr(X1), X.shape[0], _lib.ptr(Z), _lib.ptr(Z1),
+        Z.shape[0] if Z is not None else 0, float(alpha), float(beta), _lib.ptr(bias), int(act), out.data_ptr(),
+        graph.partial(d).data_ptr(), graph.counters.data_ptr(), _lib.stream_ptr()), "fr_spmm_csr_f32")
     if prof is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
@@ -61,15 +65,17 @@ def spmm(graph: PropGraph, X: torch.Tensor, Z: torch.Tensor | None = None, alpha
     return out
 
 
-def propagate_mean_raw(graph: PropGraph, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
-    """`mean_{l=0..L} S^l ego` in Horner form, L fused launches, no layer stack in memory."""
+def propagate_mean_raw(graph: PropGraph, ego: torch.Tensor, n_layers: int, ego1: torch.Tensor | None = None) -> torch.Tensor:
+    """`mean_{l=0..L} S^l [ego; ego1]` in Horner form, L fused launches, no layer stack (and no
+    concatenated ego table) in memory."""
     if n_layers == 0:
-        return ego.clone()
+        return ego.clone() if ego1 is None else torch.cat((ego, ego1), 0)
     inv = 1.0 / (n_layers + 1)
-    t = ego
+    t, t1 = ego, ego1
     for layer in range(n_layers):
         last = layer == n_layers - 1
-        t = spmm(graph, t, Z=ego, alpha=inv if last else 1.0, beta=inv if last else 1.0)
+        t = spmm(graph, t, Z=ego, alpha=inv if last else 1.0, beta=inv if last else 1.0, X1=t1, Z1=ego1)
+        t1 = None
     return t
 
 
@@ -88,9 +94,31 @@ class _PropagateMean(torch.autograd.Function):
         return propagate_mean_raw(gt, g.contiguous(), ctx.n_layers), None, None
 
 
-def propagate_mean(graph: PropGraph, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
-    """Differentiable layer-mean propagation (replaces the `torch.sparse.mm` loop + stack/mean)."""
-    return _PropagateMean.apply(ego, graph, n_layers)
+class _PropagateMean2(torch.autograd.Function):
+    """Layer-mean propagation of the stacked table [top; bottom] without building it; the gradient is one
+    buffer whose two row blocks are handed back as views."""
+
+    @staticmethod
+    def forward(ctx, top, bottom, graph, n_layers):
+        ctx.graph, ctx.n_layers, ctx.n_top = graph, n_layers, top.shape[0]
+        return propagate_mean_raw(graph, top.contiguous(), n_layers, bottom.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        gt = ctx.graph.T
+        if gt is None:
+            raise _lib.FoodRecError("graph has no transpose plan; build it with a `.T`")
+        r = propagate_mean_raw(gt, g.contiguous(), ctx.n_layers)
+        return r[:ctx.n_top], r[ctx.n_top:], None, None
+
+
+def propagate_mean(graph: PropGraph, ego: torch.Tensor, n_layers: int, bottom: torch.Tensor | None = None) -> torch.Tensor:
+    """Differentiable layer-mean propagation (replaces the `torch.sparse.mm` loop + stack/mean).  With
+    `bottom`, the propagated table is `[ego; bottom]` (the reference's `torch.cat` of two tables) read in
+    place."""
+    if bottom is None:
+        return _PropagateMean.apply(ego, graph, n_layers)
+    return _PropagateMean2.apply(ego, bottom, graph, n_layers)
 
 
 class _SpmmBiasTanh(torch.autograd.Function):
@@ -161,17 +189,22 @@ class _RankLoss(torch.autograd.Function):
         reg_tabs = ctx.saved_tensors[6 + ng:6 + 2 * ng]
         B, d = u.numel(), emb.shape[1]
         g_out = torch.stack([g_mf.reshape(()), g_reg.reshape(())]).to(torch.float32).contiguous()
-        d_emb = torch.zeros_like(emb) if ctx.needs_input_grad[0] else None
-        # one dense gradient per distinct table (the same table may back several groups)
-        uniq, d_tabs = {}, []
+        # one zero-filled allocation (one fill launch) holds d_emb and one dense gradient per distinct
+        # regulariser table (the same table may back several groups)
+        shapes = [emb.shape] if ctx.needs_input_grad[0] else []
+        keys = []
         for k, t in enumerate(reg_tabs):
-            if not ctx.needs_input_grad[9 + k]:
-                d_tabs.append(None)
-                continue
-            key = t.data_ptr()
-            if key not in uniq:
-                uniq[key] = torch.zeros_like(t)
-            d_tabs.append(uniq[key])
+            if ctx.needs_input_grad[9 + k] and t.data_ptr() not in keys:
+                keys.append(t.data_ptr())
+                shapes.append(t.shape)
+        flat = torch.zeros(sum(sh[0] * sh[1] for sh in shapes), dtype=torch.float32, device=emb.device)
+        views, o = [], 0
+        for sh in shapes:
+            views.append(flat[o:o + sh[0] * sh[1]].view(sh[0], sh[1]))
+            o += sh[0] * sh[1]
+        d_emb = views.pop(0) if ctx.needs_input_grad[0] else None
+        uniq = dict(zip(keys, views))
+        d_tabs = [uniq[t.data_ptr()] if ctx.needs_input_grad[9 + k] else None for k, t in enumerate(reg_tabs)]
         cnt = (C.c_int64 * max(ng, 1))(*[int(i.numel()) for i in reg_idx])
         pad = (C.c_int64 * max(ng, 1))(*pads)
         _lib.check(_L.fr_rank_loss_bwd(
@@ -256,45 +289,114 @@ def _dcor_ws(device, n):
     return ws
 
 
+def _dcor_forward(tabs, idx, pairs, scale):
+    V, P, n, d = len(tabs), len(pairs), idx.numel(), tabs[0].shape[1]
+    for t in tabs:
+        _chk_f32(t, "view table")
+    dev = tabs[0].device
+    Dm = torch.empty((V, n, n), dtype=torch.float32, device=dev)
+    rowmean = torch.empty((V, n), dtype=torch.float32, device=dev)
+    out = torch.empty(P + 1, dtype=torch.float32, device=dev)
+    dfds = torch.empty(3 * P, dtype=torch.float32, device=dev)
+    gm = torch.empty(V, dtype=torch.float32, device=dev)
+    pr = (C.c_int32 * (2 * P))(*[int(x) for ab in pairs for x in ab])
+    _lib.check(_L.fr_dcor_fwd(_ptr_array(tabs), V, d, idx.data_ptr(), n, pr, P, float(scale), Dm.data_ptr(),
+                              rowmean.data_ptr(), out.data_ptr(), dfds.data_ptr(), gm.data_ptr(),
+                              _dcor_ws(dev, n).data_ptr(), _lib.stream_ptr()), "fr_dcor_fwd")
+    return out, (Dm, rowmean, dfds, gm)
+
+
+def _dcor_backward(tabs, idx, pairs, state, g_terms, d_tabs):
+    """Accumulates sum_p g_terms[p] * d term_p / d tab_v into the dense `d_tabs[v]` (None = skip)."""
+    Dm, rowmean, dfds, gm = state
+    V, P, n, d = len(tabs), len(pairs), idx.numel(), tabs[0].shape[1]
+    pr = (C.c_int32 * (2 * P))(*[x for ab in pairs for x in ab])
+    _lib.check(_L.fr_dcor_bwd(_ptr_array(tabs), V, d, idx.data_ptr(), n, pr, P, Dm.data_ptr(), rowmean.data_ptr(),
+                              dfds.data_ptr(), gm.data_ptr(), g_terms.data_ptr(), _ptr_array(d_tabs),
+                              _lib.stream_ptr()), "fr_dcor_bwd")
+
+
+def _term_grads(g_terms, g_total, P):
+    """Upstream gradient per term: explicit per-term gradients plus the gradient of their sum."""
+    if g_terms is None:
+        return g_total.to(torch.float32).reshape(1).expand(P).contiguous()
+    g = g_terms.to(torch.float32)
+    if g_total is not None:
+        g = g + g_total.reshape(1)
+    return g.contiguous()
+
+
 class _DcorTerms(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, idx, pairs, *tabs):
-        V, P, n, d = len(tabs), len(pairs), idx.numel(), tabs[0].shape[1]
-        for t in tabs:
-            _chk_f32(t, "view table")
-        dev = tabs[0].device
-        Dm = torch.empty((V, n, n), dtype=torch.float32, device=dev)
-        rowmean = torch.empty((V, n), dtype=torch.float32, device=dev)
-        out = torch.empty(P, dtype=torch.float32, device=dev)
-        dfds = torch.empty(3 * P, dtype=torch.float32, device=dev)
-        gm = torch.empty(V, dtype=torch.float32, device=dev)
-        pr = (C.c_int32 * (2 * P))(*[int(x) for ab in pairs for x in ab])
-        _lib.check(_L.fr_dcor_fwd(_ptr_array(tabs), V, d, idx.data_ptr(), n, pr, P, Dm.data_ptr(), rowmean.data_ptr(),
-                                  out.data_ptr(), dfds.data_ptr(), gm.data_ptr(), _dcor_ws(dev, n).data_ptr(),
-                                  _lib.stream_ptr()), "fr_dcor_fwd")
-        ctx.save_for_backward(idx, Dm, rowmean, dfds, gm, *tabs)
-        ctx.pairs = [tuple(int(x) for x in ab) for ab in pairs]
-        return out
+    """(terms [P], their sum [1]) -- both scaled by `scale` inside the kernel."""
 
     @staticmethod
-    def backward(ctx, g):
-        idx, Dm, rowmean, dfds, gm = ctx.saved_tensors[:5]
-        tabs = ctx.saved_tensors[5:]
-        V, P, n, d = len(tabs), len(ctx.pairs), idx.numel(), tabs[0].shape[1]
-        g = g.to(torch.float32).contiguous()
-        d_tabs = [torch.zeros_like(t) if ctx.needs_input_grad[2 + k] else None for k, t in enumerate(tabs)]
-        pr = (C.c_int32 * (2 * P))(*[x for ab in ctx.pairs for x in ab])
-        _lib.check(_L.fr_dcor_bwd(_ptr_array(tabs), V, d, idx.data_ptr(), n, pr, P, Dm.data_ptr(), rowmean.data_ptr(),
-                                  dfds.data_ptr(), gm.data_ptr(), g.data_ptr(), _ptr_array(d_tabs),
-                                  _lib.stream_ptr()), "fr_dcor_bwd")
-        return (None, None, *d_tabs)
+    def forward(ctx, idx, pairs, scale, *tabs):
+        pairs = [tuple(int(x) for x in ab) for ab in pairs]
+        out, state = _dcor_forward(tabs, idx, pairs, scale)
+        ctx.save_for_backward(idx, *state, *tabs)
+        ctx.pairs = pairs
+        return out[:len(pairs)], out[len(pairs):]
+
+    @staticmethod
+    def backward(ctx, g_terms, g_total):
+        idx = ctx.saved_tensors[0]
+        state, tabs = ctx.saved_tensors[1:5], ctx.saved_tensors[5:]
+        g = _term_grads(g_terms, g_total, len(ctx.pairs))
+        d_tabs = [torch.zeros_like(t) if ctx.needs_input_grad[3 + k] else None for k, t in enumerate(tabs)]
+        _dcor_backward(tabs, idx, ctx.pairs, state, g, d_tabs)
+        return (None, None, None, *d_tabs)
 
 
-def dcor_terms(tabs, idx: torch.Tensor, pairs) -> torch.Tensor:
-    """Distance correlations `[P]` between the views `tabs[v][idx]` for the view pairs `pairs`
-    (FoodRec/models/pricai_modelx.py:245-247,263,409-437): gathers, distance matrices, centring,
-    covariances and their backward in four launches."""
-    return _DcorTerms.apply(_idx(idx.reshape(-1), "idx"), list(pairs), *[t.contiguous() for t in tabs])
+def dcor_terms(tabs, idx: torch.Tensor, pairs, scale: float = 1.0, with_total: bool = False):
+    """Distance correlations `[P]` (times `scale`) between the views `tabs[v][idx]` for the view pairs
+    `pairs` (FoodRec/models/pricai_modelx.py:245-247,263,409-437): gathers, distance matrices, centring,
+    covariances and their backward in four launches.  `with_total=True` also returns their sum `[1]`."""
+    terms, total = _DcorTerms.apply(_idx(idx.reshape(-1), "idx"), list(pairs), float(scale), *[t.contiguous() for t in tabs])
+    return (terms, total) if with_total else terms
+
+
+class _ItemViews(torch.autograd.Function):
+    """CLUSSL's consumer of the three item-side tables, fused: `item_emb = sum_v tab_v[:n_items]`
+    (pricai_modelx.py:219) and the scaled distance-correlation total over the rows `idx` (:245-263).  The
+    backward writes each table's dense gradient once (`rows < n_items` take the item_emb gradient, the rest
+    zero) and lets the dcor backward accumulate into it: 2 launches instead of 3 x (zeros + slice copy) +
+    3 zeros + 3 adds."""
+
+    @staticmethod
+    def forward(ctx, idx, pairs, scale, n_items, *tabs):
+        pairs = [tuple(int(x) for x in ab) for ab in pairs]
+        out, state = _dcor_forward(tabs, idx, pairs, scale)
+        d = tabs[0].shape[1]
+        item_emb = torch.empty((n_items, d), dtype=torch.float32, device=tabs[0].device)
+        _lib.check(_L.fr_sum_rows(_ptr_array(tabs), len(tabs), d, n_items, item_emb.data_ptr(), _lib.stream_ptr()),
+                   "fr_sum_rows")
+        ctx.save_for_backward(idx, *state, *tabs)
+        ctx.pairs, ctx.n_items = pairs, n_items
+        return item_emb, out[len(pairs):]
+
+    @staticmethod
+    def backward(ctx, g_item, g_total):
+        idx = ctx.saved_tensors[0]
+        state, tabs = ctx.saved_tensors[1:5], ctx.saved_tensors[5:]
+        d = tabs[0].shape[1]
+        d_tabs = [torch.empty_like(t) for t in tabs]
+        if g_item is None:
+            for t in d_tabs:
+                t.zero_()
+        else:
+            rows = (C.c_int64 * len(tabs))(*[int(t.shape[0]) for t in tabs])
+            g_item = g_item.contiguous()
+            _lib.check(_L.fr_spread_rows(g_item.data_ptr(), d, ctx.n_items, _ptr_array(d_tabs), rows, len(tabs),
+                                         _lib.stream_ptr()), "fr_spread_rows")
+        if g_total is not None:
+            _dcor_backward(tabs, idx, ctx.pairs, state, _term_grads(None, g_total, len(ctx.pairs)), d_tabs)
+        return (None, None, None, None, *d_tabs)
+
+
+def item_views(tabs, idx: torch.Tensor, pairs, scale: float, n_items: int):
+    """`(sum_v tabs[v][:n_items], scale * sum_p dcor_p)` with the fused backward described above."""
+    return _ItemViews.apply(_idx(idx.reshape(-1), "idx"), list(pairs), float(scale), int(n_items),
+                            *[t.contiguous() for t in tabs])
 
 
 def correlation_distance(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -55,8 +55,8 @@ def spmm(graph: PropGraph, X: torch.Tensor, Z: torch.Tensor | None = None, alpha
         ev0.record()
     _lib.check(_L.fr_spmm_csr_f32_split(
         graph.seg.data_ptr(), graph.n_seg, graph.long_rows.data_ptr(), graph.n_long, graph.col.data_ptr(),
-        graph.val.data_ptr(), d, X.data_ptr(), _lib.ptr(X1), X.shape[0], _lib.ptr(Z), _lib.ptr(Z1),
-        Z.shape[0] if Z is not None else 0, float(alpha), float(beta), _lib.ptr(bias), int(act), out.data_ptr(),
+        graph.val.data_ptr(), d, X.data_ptr(), _lib.ptr(X1), X.shape[0] if X1 is not None else 0, _lib.ptr(Z), _lib.ptr(Z1),
+        Z.shape[0] if (Z is not None and Z1 is not None) else 0, float(alpha), float(beta), _lib.ptr(bias), int(act), out.data_ptr(),
         graph.partial(d).data_ptr(), graph.counters.data_ptr(), _lib.stream_ptr()), "fr_spmm_csr_f32")
     if prof is not None:
         ev1 = torch.cuda.Event(enable_timing=True)

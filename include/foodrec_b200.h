@@ -125,7 +125,7 @@ int fr_csr_from_coo(const int64_t *coo_rows, int64_t nnz, int32_t n_rows, int32_
  * zero fill of up to four tables in one launch). */
 int fr_sum_rows(const float *const *tab_host, int32_t n_tabs, int32_t d, int64_t rows, float *out, void *stream);
 int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *const *d_tab_host, const int64_t *rows_total_host,
-                   int32_t n_tabs, void *stream);
+                   int32_t n_tabs, int32_t accumulate /* 1: d_tab_v[r] += g[r] for r < rows only */, void *stream);
 
 /* Row gather out[r] = tab[idx[r]] and its adjoint d_tab[idx[r]] += g[r] (fp32 atomics).
  * Replaces `E[idx]` indexing at pricai_modelx.py:245-247 and the candidate gathers of

@@ -142,10 +142,18 @@ __global__ void sum_rows_kernel(Tabs4 t, long long n4, float *__restrict__ out) 
         reinterpret_cast<float4 *>(out)[i] = a;
     }
 }
-__global__ void spread_rows_kernel(Tabs4 t, long long n4_src, const float *__restrict__ g) {
+__global__ void spread_rows_kernel(Tabs4 t, long long n4_src, const float *__restrict__ g, int accumulate) {
     const int v = blockIdx.y;
     float4 *dst = reinterpret_cast<float4 *>(t.out[v]);
     if (dst == nullptr) return;
+    if (accumulate) {            // d_tab_v[r] += g[r] for r < rows; the rest already holds its value
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_src; i += (long long)gridDim.x * blockDim.x) {
+            float4 a = dst[i];
+            fr::add4(a, fr::ldg_f4(g + 4 * i));
+            dst[i] = a;
+        }
+        return;
+    }
     const long long tot4 = t.rows_total[v];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot4; i += (long long)gridDim.x * blockDim.x)
         dst[i] = i < n4_src ? fr::ldg_f4(g + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -168,7 +176,7 @@ extern "C" int fr_sum_rows(const float *const *tab_host, int32_t n_tabs, int32_t
 }
 
 extern "C" int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *const *d_tab_host, const int64_t *rows_total_host,
-                              int32_t n_tabs, void *stream) {
+                              int32_t n_tabs, int32_t accumulate, void *stream) {
     FR_REQUIRE(n_tabs >= 1 && n_tabs <= 4 && d > 0 && d % 4 == 0 && rows >= 0 && g && d_tab_host && rows_total_host,
                "fr_spread_rows: bad argument");
     Tabs4 t{};
@@ -182,6 +190,6 @@ extern "C" int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *co
     }
     if (mx == 0) return FR_OK;
     fr::LaunchTimer _lt("spread_rows_kernel", (cudaStream_t)stream);
-    spread_rows_kernel<<<dim3(grid1d(mx, 256), n_tabs), 256, 0, (cudaStream_t)stream>>>(t, rows * (d / 4), g);
+    spread_rows_kernel<<<dim3(grid1d(mx, 256), n_tabs), 256, 0, (cudaStream_t)stream>>>(t, rows * (d / 4), g, accumulate);
     return fr::check_launch("fr_spread_rows");
 }

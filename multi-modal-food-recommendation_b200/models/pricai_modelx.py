@@ -133,13 +133,20 @@ class PRICAI_ModelX(DotProductRecommender):
         # The views are rows `all_item` (< n_items) of the propagated [I + C, d] tables, gathered in-kernel:
         # loss_cl * (dcor(image, text) + dcor(image, ingre) + dcor(ingre, text)), fused with
         # item_emb = ingre[:I] + image[:I] + text[:I]; `loss_cl` and `reg_weight` are folded into the kernels.
+        fork = getattr(self, "fork_streams", True)
+
         def views(img, txt, ing):
-            return ops.item_views([img, txt, ing], all_item, [(0, 1), (0, 2), (2, 1)], self.loss_cl, self.n_items)
+            return ops.item_views([img, txt, ing], all_item, [(0, 1), (0, 2), (2, 1)], self.loss_cl, self.n_items,
+                                  side_stream=self._side_streams()[0] if fork else None)
         all_emb, _, cl_loss = self._propagate_all(side_fn=views)
         uw, iw = self.user_embedding.weight, self.item_embedding.weight
         mf_loss_g, reg = ops.rank_loss(all_emb, self.n_users, user, pos_item, neg_item,
                                        [(uw, user), (iw, pos_item), (iw, neg_item)],
                                        reg_den=float(neg_item.shape[0]) / self.reg_weight, gamma=self.mf_loss.gamma)
+        if fork:   # join the contrastive branch before the caller combines the terms
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self._side_streams()[0])
+            cl_loss.record_stream(cur)
         return mf_loss_g, cl_loss, reg.reshape(1)
 
     def CL_loss(self, hidden, hidden_norm=True, temperature=0.5):

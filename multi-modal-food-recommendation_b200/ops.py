@@ -355,48 +355,92 @@ def dcor_terms(tabs, idx: torch.Tensor, pairs, scale: float = 1.0, with_total: b
     return (terms, total) if with_total else terms
 
 
-class _ItemViews(torch.autograd.Function):
-    """CLUSSL's consumer of the three item-side tables, fused: `item_emb = sum_v tab_v[:n_items]`
-    (pricai_modelx.py:219) and the scaled distance-correlation total over the rows `idx` (:245-263).  The
-    backward writes each table's dense gradient once (`rows < n_items` take the item_emb gradient, the rest
-    zero) and lets the dcor backward accumulate into it: 2 launches instead of 3 x (zeros + slice copy) +
-    3 zeros + 3 adds."""
+class _GradHolder:
+    """Hand-over between the two halves of `item_views` in the backward: the contrastive half runs first
+    (its upstream gradient is known at the start of the backward) on its own stream and parks the dense
+    table gradients here; the item_emb half adds its rows to them and returns them.  Either order of the
+    two backward calls gives the same gradients."""
 
+    def __init__(self):
+        self.d_tabs = None
+        self.stream = None
+        self.done = False
+        self.consumed = False
+
+
+class _DcorTotalInto(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, idx, pairs, scale, n_items, *tabs):
+    def forward(ctx, idx, pairs, scale, holder, *tabs):
         pairs = [tuple(int(x) for x in ab) for ab in pairs]
         out, state = _dcor_forward(tabs, idx, pairs, scale)
-        d = tabs[0].shape[1]
-        item_emb = torch.empty((n_items, d), dtype=torch.float32, device=tabs[0].device)
-        _lib.check(_L.fr_sum_rows(_ptr_array(tabs), len(tabs), d, n_items, item_emb.data_ptr(), _lib.stream_ptr()),
-                   "fr_sum_rows")
         ctx.save_for_backward(idx, *state, *tabs)
-        ctx.pairs, ctx.n_items = pairs, n_items
-        return item_emb, out[len(pairs):]
+        ctx.pairs, ctx.holder = pairs, holder
+        return out[len(pairs):]
 
     @staticmethod
-    def backward(ctx, g_item, g_total):
+    def backward(ctx, g_total):
         idx = ctx.saved_tensors[0]
         state, tabs = ctx.saved_tensors[1:5], ctx.saved_tensors[5:]
+        h = ctx.holder
+        d_tabs = [torch.zeros_like(t) for t in tabs]
+        _dcor_backward(tabs, idx, ctx.pairs, state, _term_grads(None, g_total, len(ctx.pairs)), d_tabs)
+        if h.consumed:                       # the other half already ran: ordinary gradients, autograd adds them
+            return (None, None, None, None, *d_tabs)
+        h.d_tabs, h.stream, h.done = d_tabs, torch.cuda.current_stream(), True
+        return (None, None, None, None) + (None,) * len(tabs)
+
+
+class _SumRowsInto(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, n_items, holder, *tabs):
         d = tabs[0].shape[1]
-        d_tabs = [torch.empty_like(t) for t in tabs]
-        if g_item is None:
-            for t in d_tabs:
-                t.zero_()
+        for t in tabs:
+            _chk_f32(t, "table")
+        out = torch.empty((n_items, d), dtype=torch.float32, device=tabs[0].device)
+        _lib.check(_L.fr_sum_rows(_ptr_array(tabs), len(tabs), d, n_items, out.data_ptr(), _lib.stream_ptr()), "fr_sum_rows")
+        ctx.n_items, ctx.holder = n_items, holder
+        ctx.shapes = [tuple(t.shape) for t in tabs]
+        ctx.dev = tabs[0].device
+        return out
+
+    @staticmethod
+    def backward(ctx, g_item):
+        h, d = ctx.holder, ctx.shapes[0][1]
+        g_item = g_item.contiguous()
+        rows = (C.c_int64 * len(ctx.shapes))(*[int(sh[0]) for sh in ctx.shapes])
+        if h.done and not h.consumed:        # add to the parked contrastive gradients (other stream: join first)
+            cur = torch.cuda.current_stream()
+            if h.stream is not None and h.stream != cur:
+                cur.wait_stream(h.stream)
+                for t in h.d_tabs:
+                    t.record_stream(cur)
+            d_tabs, acc = h.d_tabs, 1
         else:
-            rows = (C.c_int64 * len(tabs))(*[int(t.shape[0]) for t in tabs])
-            g_item = g_item.contiguous()
-            _lib.check(_L.fr_spread_rows(g_item.data_ptr(), d, ctx.n_items, _ptr_array(d_tabs), rows, len(tabs),
-                                         _lib.stream_ptr()), "fr_spread_rows")
-        if g_total is not None:
-            _dcor_backward(tabs, idx, ctx.pairs, state, _term_grads(None, g_total, len(ctx.pairs)), d_tabs)
-        return (None, None, None, None, *d_tabs)
+            d_tabs, acc = [torch.empty(sh, dtype=torch.float32, device=ctx.dev) for sh in ctx.shapes], 0
+        h.consumed = True
+        _lib.check(_L.fr_spread_rows(g_item.data_ptr(), d, ctx.n_items, _ptr_array(d_tabs), rows, len(d_tabs), acc,
+                                     _lib.stream_ptr()), "fr_spread_rows")
+        return (None, None, *d_tabs)
 
 
-def item_views(tabs, idx: torch.Tensor, pairs, scale: float, n_items: int):
-    """`(sum_v tabs[v][:n_items], scale * sum_p dcor_p)` with the fused backward described above."""
-    return _ItemViews.apply(_idx(idx.reshape(-1), "idx"), list(pairs), float(scale), int(n_items),
-                            *[t.contiguous() for t in tabs])
+def item_views(tabs, idx: torch.Tensor, pairs, scale: float, n_items: int, side_stream=None):
+    """CLUSSL's consumer of the three item-side tables: `(sum_v tabs[v][:n_items], scale * sum_p dcor_p)`
+    (pricai_modelx.py:219,245-263).  The contrastive half is latency-bound, so it is launched on
+    `side_stream` (forward and, through autograd, backward) beside the user-item propagation; in the
+    backward its dense table gradients are written once and the item_emb gradient is added to their first
+    `n_items` rows in place -- no slice copies, no extra zero fills, no gradient-sum kernels."""
+    tabs = [t.contiguous() for t in tabs]
+    idx = _idx(idx.reshape(-1), "idx")
+    holder = _GradHolder()
+    item_emb = _SumRowsInto.apply(int(n_items), holder, *tabs)
+    if side_stream is None:
+        total = _DcorTotalInto.apply(idx, list(pairs), float(scale), holder, *tabs)
+    else:
+        cur = torch.cuda.current_stream()
+        side_stream.wait_stream(cur)
+        with torch.cuda.stream(side_stream):
+            total = _DcorTotalInto.apply(idx, list(pairs), float(scale), holder, *tabs)
+    return item_emb, total
 
 
 def correlation_distance(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -311,7 +311,7 @@ spmm_bulk_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__re
 // per-row bookkeeping of the warp-per-segment kernel (D = 64: 8 lanes x 2 float4, four rows per warp),
 // and the shuffle / address / predicate work of a step is shared by 4 nonzeros.  Groups of one warp take
 // adjacent segments of the length-sorted plan, so their trip counts match.
-template <int D, int LPR, int U, int ACT>
+template <int D, int LPR, int U, int ACT, bool SPLIT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
                   const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
@@ -354,7 +354,7 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
                 const int e = j + u;
                 const int cj = __shfl_sync(0xffffffffu, c, e, LPR);
                 vv[u] = __shfl_sync(0xffffffffu, v, e, LPR);
-                const float *xr = (cj < sp.x_split ? Xo : X1o) + (size_t)cj * D;
+                const float *xr = ((!SPLIT || cj < sp.x_split) ? Xo : X1o) + (size_t)cj * D;
                 if (e < cnt) {
 #pragma unroll
                     for (int t = 0; t < VPL; ++t) x[u][t] = fr::ldg_f4(xr + 4 * LPR * t);
@@ -423,8 +423,12 @@ int launch_group_shape(const int4 *seg, int64_t n_seg, const int4 *lrows, const 
         return FR_EUNSUPPORTED;
     }
     fr::LaunchTimer _lt("spmm_group_kernel", st);
-    spmm_group_kernel<D, LPR, U, ACT><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-        seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
+    if (sp.x_split != 0x7fffffff)   // two-segment gather only where it is used (first layer of a forward)
+        spmm_group_kernel<D, LPR, U, ACT, true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+            seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
+    else
+        spmm_group_kernel<D, LPR, U, ACT, false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+            seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
     return fr::check_launch("fr_spmm_csr_f32(group)");
 }
 

@@ -474,6 +474,7 @@ struct Params2 {
     int two_pass;
 };
 
+template <bool AFFINE>   // AFFINE: scores are scale * acc + bias[col]; the plain instantiation carries none of that code
 __global__ void __launch_bounds__(THREADS2, 1)
 gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params2 PP) {
     const Params &P = PP.p;
@@ -573,12 +574,16 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (n_pass == 2) {
                 // ---------------- pass 0: group maxima -> lower bound of the k-th eligible score
                 float gmax = -INFINITY;
-                int gcur = 0;
+                // group id of (tile nb, quarter q) = floor((4 nb + q) NG / (4 n_nblk)), advanced incrementally:
+                // num = (4 nb + q) NG - gid * den stays in [0, den) (no per-tile 64-bit division)
+                const long long den = 4LL * n_nblk;
+                int gid = (int)(((long long)q * NG) / den);
+                long long num = (long long)q * NG - (long long)gid * den;
+                int gcur = gid;
                 for (int nb = 0; nb < n_nblk; ++nb) {
                     if (lane == 0) mbar_wait(tfull + as, aphase);
                     __syncwarp();
                     tc_fence_after();
-                    const int gid = (int)(((long long)(nb * 4 + q) * NG) / (4LL * n_nblk));
                     if (gid != gcur) {
                         if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
                         gmax = -INFINITY;
@@ -591,13 +596,13 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tmem_ld32(tbase + c * 32, r);
                         const int col0 = nb * BN + c * 32;
                         if (col0 >= P.N) break;
-                        if (P.bias != nullptr) {
+                        if (AFFINE && P.bias != nullptr) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 const int col = col0 + j;
                                 r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
                             }
-                        } else if (P.scale != 1.f) {
+                        } else if (AFFINE && P.scale != 1.f) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) r[j] *= P.scale;
                         }
@@ -620,6 +625,8 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty + as);
                     if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+                    num += 4LL * NG;                      // next tile: (4 (nb + 1) + q) NG
+                    while (num >= den) { num -= den; ++gid; }
                 }
                 if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
                 __threadfence_block();
@@ -669,13 +676,13 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tmem_ld32(tbase + c * 32, r);
                     const int col0 = nb * BN + c * 32;
                     if (col0 >= P.N) break;
-                    if (P.bias != nullptr) {
+                    if (AFFINE && P.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int col = col0 + j;
                             r[j] = fmaf(r[j], P.scale, col < P.N ? __ldg(P.bias + col) : 0.f);
                         }
-                    } else if (P.scale != 1.f) {
+                    } else if (AFFINE && P.scale != 1.f) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) r[j] *= P.scale;
                     }
@@ -929,7 +936,9 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
                    (long long)need, (long long)ws_bytes);
         static bool attr2 = false;
         if (!attr2) {
-            cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
+            cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(gemm_topk_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
             if (e != cudaSuccess) {
                 fr::set_error("fr_gemm_topk_bf16: cannot reserve %d bytes of shared memory: %s", SMEM2, cudaGetErrorString(e));
                 return FR_ECUDA;
@@ -944,7 +953,10 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
         Params2 P2{P, reinterpret_cast<float *>(ws),
                    reinterpret_cast<int *>(reinterpret_cast<float *>(ws) + (size_t)grid * BM * 4 * CAPG), two_pass};
         fr::LaunchTimer _lt2("gemm_topk_kernel_v2", (cudaStream_t)stream);
-        gemm_topk_kernel_v2<<<grid, THREADS2, SMEM2, (cudaStream_t)stream>>>(ma, mb, P2);
+        if (bias != nullptr || scale != 1.f)
+            gemm_topk_kernel_v2<true><<<grid, THREADS2, SMEM2, (cudaStream_t)stream>>>(ma, mb, P2);
+        else
+            gemm_topk_kernel_v2<false><<<grid, THREADS2, SMEM2, (cudaStream_t)stream>>>(ma, mb, P2);
         return fr::check_launch("fr_gemm_topk_bf16(v2)");
     }
     fr::LaunchTimer _lt("gemm_topk_kernel", (cudaStream_t)stream);

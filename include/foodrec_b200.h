@@ -81,6 +81,15 @@ int fr_spmm_csr_f32_split(const int32_t *seg, int64_t n_seg, const int32_t *long
                           int32_t x_split, const float *Z0, const float *Z1, int32_t z_split, float alpha, float beta,
                           const float *bias, int32_t act, float *Y, float *partial, int32_t *counters, void *stream);
 
+/* Backward-pass variant with row-activity masks: x_mask[c] == 0 promises that row c of X is exactly zero (its
+ * gather is skipped); y_mask[r] (optional) receives whether output row r has a nonzero.  The gradient of a
+ * mini-batch ranking loss touches <= 3 B rows, so the first backward layers gather a small fraction of the
+ * table.  Results are bit-identical to the unmasked call. */
+int fr_spmm_csr_f32_masked(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                           const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z,
+                           float alpha, float beta, float *Y, float *partial, int32_t *counters, const uint8_t *x_mask,
+                           uint8_t *y_mask, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused ranking loss on gathered rows: BPR + embedding regulariser, forward and backward.
  * Replaces the gathers, `torch.mul(..).sum(1)`, `BPRLoss` and `EmbLoss` at
@@ -112,7 +121,8 @@ int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, const int64_
                      const int64_t *n, int32_t B, const float *coef, const float *g_out, float *d_emb,
                      int32_t n_groups, const float *const *reg_tab_host, const int64_t *const *reg_idx_host,
                      const int64_t *reg_cnt_host, const int64_t *reg_pad_host, float reg_den,
-                     const float *gnorm, float *const *d_tab_host, void *stream);
+                     const float *gnorm, float *const *d_tab_host, uint8_t *emb_mask /* [n_rows] zeroed, or NULL */,
+                     void *stream);
 
 /* Row pointers of a CSR from the row indices of a COO (any order; for a row-major-sorted COO -- what the
  * reference builds, FoodRec/models/cikm_model.py:174-180 -- `col`/`val` are then already in CSR order).
@@ -125,7 +135,9 @@ int fr_csr_from_coo(const int64_t *coo_rows, int64_t nnz, int32_t n_rows, int32_
  * zero fill of up to four tables in one launch). */
 int fr_sum_rows(const float *const *tab_host, int32_t n_tabs, int32_t d, int64_t rows, float *out, void *stream);
 int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *const *d_tab_host, const int64_t *rows_total_host,
-                   int32_t n_tabs, int32_t accumulate /* 1: d_tab_v[r] += g[r] for r < rows only */, void *stream);
+                   int32_t n_tabs, int32_t accumulate /* 1: d_tab_v[r] += g[r] for r < rows only */,
+                   const uint8_t *src_mask /* row mask of g or NULL (= all active) */,
+                   uint8_t *const *mask_host /* per-table row masks to write / OR into, or NULL */, void *stream);
 
 /* Row gather out[r] = tab[idx[r]] and its adjoint d_tab[idx[r]] += g[r] (fp32 atomics).
  * Replaces `E[idx]` indexing at pricai_modelx.py:245-247 and the candidate gathers of
@@ -155,7 +167,8 @@ int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, const int64_
                 float *dfds, float *gm, float *ws, void *stream);
 int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
                 const int32_t *pairs_host, int32_t P, const float *Dm, const float *rowmean,
-                const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host, void *stream);
+                const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host,
+                uint8_t *const *mask_host /* optional: mark the rows idx[] of each table's mask */, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ranking: scores = scale * A . B^T + bias  ->  per-row top-k, never materialising [M, N].

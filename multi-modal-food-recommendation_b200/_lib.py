@@ -42,12 +42,13 @@ SIGNATURES = {
                                         _p, _p, _p, _p]),
     "fr_rank_loss_ws_floats": (_i64, []),
     "fr_rank_loss_fwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
-    "fr_rank_loss_bwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _f32, _p, _p, _p]),
+    "fr_rank_loss_bwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _p]),
+    "fr_spmm_csr_f32_masked": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i32, _p, _p, _f32, _f32, _p, _p, _p, _p, _p, _p]),
     "fr_dcor_ws_floats": (_i64, [_i32]),
     "fr_dcor_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p, _p, _p]),
     "fr_sum_rows": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
-    "fr_spread_rows": (C.c_int, [_p, _i32, _i64, _p, _p, _i32, _i32, _p]),
-    "fr_dcor_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "fr_spread_rows": (C.c_int, [_p, _i32, _i64, _p, _p, _i32, _i32, _p, _p, _p]),
+    "fr_dcor_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "fr_f32_to_bf16": (C.c_int, [_p, _p, _i64, _i32, _i32, _p]),
     "fr_gemm_topk_ws_bytes": (_i64, [_i32]),
     "fr_gemm_topk_bf16": (C.c_int, [_p, _i32, _p, _i32, _i32, _f32, _p, _p, _p, _p, _i32, _p, _p, _p, _i64, _p]),

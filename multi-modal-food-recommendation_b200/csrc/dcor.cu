@@ -28,6 +28,7 @@ constexpr float kEpsD = 1e-8f;
 struct Views {
     const float *tab[kMaxV];
     float *dtab[kMaxV];
+    unsigned char *mask[kMaxV];   // optional row-activity masks of the dense gradients
     int V;
 };
 struct Pairs {
@@ -299,6 +300,7 @@ dcor_bwd_kernel(Views vw, Pairs pr, const int64_t *__restrict__ idx, int n, cons
         const size_t row = (size_t)idx[i0 + orow];
         const float4 xi = fr::ldg_f4(tab + row * D + 4 * okq);
         float *dst = vw.dtab[v] + row * D + 4 * okq;
+        if (vw.mask[v] != nullptr && okq == 0) vw.mask[v][row] = 1;
         atomicAdd(dst + 0, 4.f * (wsum * xi.x - acc.x));
         atomicAdd(dst + 1, 4.f * (wsum * xi.y - acc.y));
         atomicAdd(dst + 2, 4.f * (wsum * xi.z - acc.z));
@@ -312,6 +314,7 @@ int fill(Views &vw, Pairs &pr, int V, const float *const *tab, float *const *dta
     for (int v = 0; v < kMaxV; ++v) {
         vw.tab[v] = v < V ? tab[v] : nullptr;
         vw.dtab[v] = (v < V && dtab) ? dtab[v] : nullptr;
+        vw.mask[v] = nullptr;
         FR_REQUIRE(v >= V || tab[v], "dcor: null view table %d", v);
     }
     pr.P = P;
@@ -363,11 +366,13 @@ extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, c
 extern "C" int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
                            const int32_t *pairs_host, int32_t P, const float *Dm, const float *rowmean,
                            const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host,
-                           void *stream) {
+                           uint8_t *const *mask_host, void *stream) {
     FR_REQUIRE(idx && Dm && rowmean && dfds && gm && g_out && d_tab_host && n > 0, "fr_dcor_bwd: bad argument");
     Views vw;
     Pairs pr;
     if (int rc = fill(vw, pr, V, tab_host, d_tab_host, P, pairs_host)) return rc;
+    if (mask_host)
+        for (int v = 0; v < V; ++v) vw.mask[v] = mask_host[v];
     cudaStream_t st = (cudaStream_t)stream;
     dim3 g((n + 15) / 16, V, 4);
     fr::LaunchTimer _lt("dcor_bwd_kernel", st);

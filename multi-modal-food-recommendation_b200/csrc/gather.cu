@@ -132,6 +132,7 @@ namespace {
 struct Tabs4 {
     const float *in[4];
     float *out[4];
+    unsigned char *mask[4];
     long long rows_total[4];
     int n;
 };
@@ -142,10 +143,20 @@ __global__ void sum_rows_kernel(Tabs4 t, long long n4, float *__restrict__ out) 
         reinterpret_cast<float4 *>(out)[i] = a;
     }
 }
-__global__ void spread_rows_kernel(Tabs4 t, long long n4_src, const float *__restrict__ g, int accumulate) {
+__global__ void spread_rows_kernel(Tabs4 t, long long n4_src, const float *__restrict__ g, int accumulate,
+                                   const unsigned char *__restrict__ src_mask, int d4) {
     const int v = blockIdx.y;
     float4 *dst = reinterpret_cast<float4 *>(t.out[v]);
     if (dst == nullptr) return;
+    if (t.mask[v] != nullptr) {     // row-activity mask of the result (one byte per row)
+        const long long rows_src = n4_src / d4, rows_tot = t.rows_total[v] / d4;
+        for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < (accumulate ? rows_src : rows_tot);
+             r += (long long)gridDim.x * blockDim.x) {
+            const unsigned char m = r < rows_src ? (src_mask ? src_mask[r] : (unsigned char)1) : (unsigned char)0;
+            if (accumulate) { if (m) t.mask[v][r] = 1; }
+            else t.mask[v][r] = m;
+        }
+    }
     if (accumulate) {            // d_tab_v[r] += g[r] for r < rows; the rest already holds its value
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_src; i += (long long)gridDim.x * blockDim.x) {
             float4 a = dst[i];
@@ -176,7 +187,8 @@ extern "C" int fr_sum_rows(const float *const *tab_host, int32_t n_tabs, int32_t
 }
 
 extern "C" int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *const *d_tab_host, const int64_t *rows_total_host,
-                              int32_t n_tabs, int32_t accumulate, void *stream) {
+                              int32_t n_tabs, int32_t accumulate, const uint8_t *src_mask, uint8_t *const *mask_host,
+                              void *stream) {
     FR_REQUIRE(n_tabs >= 1 && n_tabs <= 4 && d > 0 && d % 4 == 0 && rows >= 0 && g && d_tab_host && rows_total_host,
                "fr_spread_rows: bad argument");
     Tabs4 t{};
@@ -185,11 +197,12 @@ extern "C" int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *co
     for (int v = 0; v < n_tabs; ++v) {
         FR_REQUIRE(rows_total_host[v] >= rows, "fr_spread_rows: table %d shorter than the source", v);
         t.out[v] = d_tab_host[v];
+        t.mask[v] = mask_host ? mask_host[v] : nullptr;
         t.rows_total[v] = rows_total_host[v] * (d / 4);
         mx = std::max(mx, t.rows_total[v]);
     }
     if (mx == 0) return FR_OK;
     fr::LaunchTimer _lt("spread_rows_kernel", (cudaStream_t)stream);
-    spread_rows_kernel<<<dim3(grid1d(mx, 256), n_tabs), 256, 0, (cudaStream_t)stream>>>(t, rows * (d / 4), g, accumulate);
+    spread_rows_kernel<<<dim3(grid1d(mx, 256), n_tabs), 256, 0, (cudaStream_t)stream>>>(t, rows * (d / 4), g, accumulate, src_mask, d / 4);
     return fr::check_launch("fr_spread_rows");
 }

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 rank_loss_bwd_kernel(const float *__restrict__ emb, int d, long long item_off, const int64_t *__restrict__ u,
                      const int64_t *__restrict__ p, const int64_t *__restrict__ n, int B,
                      const float *__restrict__ coef, const float *__restrict__ g_out, float *__restrict__ d_emb,
-                     Groups g, float reg_den, const float *__restrict__ gnorm) {
+                     Groups g, float reg_den, const float *__restrict__ gnorm, unsigned char *__restrict__ emb_mask) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long n_tasks = B + g.start[g.n];
     const long long warps_total = (long long)gridDim.x * kWarps;
@@ -117,6 +117,8 @@ rank_loss_bwd_kernel(const float *__restrict__ emb, int d, long long item_off, c
             if (d_emb == nullptr) continue;
             const size_t ur = (size_t)u[t] * d, pr = (size_t)(item_off + p[t]) * d, nr = (size_t)(item_off + n[t]) * d;
             const float c = coef[t] * g_mf;
+            if (emb_mask != nullptr && lane < 3)      // rows of d_emb this triple touches (all others stay exactly 0)
+                emb_mask[lane == 0 ? u[t] : (item_off + (lane == 1 ? p[t] : n[t]))] = 1;
             for (int k = lane; k < d; k += 32) {
                 const float uv = __ldg(emb + ur + k), pv = __ldg(emb + pr + k), nv = __ldg(emb + nr + k);
                 atomicAdd(d_emb + ur + k, c * (pv - nv));
@@ -189,7 +191,7 @@ extern "C" int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, c
                                 int32_t n_groups, const float *const *reg_tab_host,
                                 const int64_t *const *reg_idx_host, const int64_t *reg_cnt_host,
                                 const int64_t *reg_pad_host, float reg_den, const float *gnorm,
-                                float *const *d_tab_host, void *stream) {
+                                float *const *d_tab_host, uint8_t *emb_mask, void *stream) {
     FR_REQUIRE(emb && u && p && n && coef && g_out && gnorm, "fr_rank_loss_bwd: null pointer");
     FR_REQUIRE(B > 0 && d > 0, "fr_rank_loss_bwd: B=%d d=%d", B, d);
     Groups g;
@@ -198,6 +200,6 @@ extern "C" int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, c
     const int grid = grid_for(B + g.start[g.n]);
     fr::LaunchTimer _lt("rank_loss_bwd_kernel", (cudaStream_t)stream);
     rank_loss_bwd_kernel<<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(emb, d, item_off, u, p, n, B, coef, g_out,
-                                                                         d_emb, g, reg_den, gnorm);
+                                                                         d_emb, g, reg_den, gnorm, emb_mask);
     return fr::check_launch("fr_rank_loss_bwd");
 }

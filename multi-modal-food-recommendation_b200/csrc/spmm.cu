@@ -28,6 +28,11 @@ struct Split {
     int x_split;
     const float *Z1_adj;
     int z_split;
+    // Optional row-activity masks (backward of a mini-batch loss: most rows of the upstream gradient are
+    // exactly zero).  x_mask[c] == 0 promises that row c of X is all zeros, so its gather is skipped;
+    // y_mask[r] receives whether output row r has any nonzero, for the next layer.
+    const unsigned char *x_mask;
+    unsigned char *y_mask;
 };
 
 template <int D>
@@ -49,7 +54,7 @@ __device__ __forceinline__ float4 reduce_subgroups(float4 a) {
 }
 
 template <int D, int ACT>
-__device__ __forceinline__ void epilogue_store(float4 acc, int row, int off, const float *__restrict__ Z,
+__device__ __forceinline__ bool epilogue_store(float4 acc, int row, int off, const float *__restrict__ Z,
                                                float alpha, float beta, const float *__restrict__ bias,
                                                float *__restrict__ Y) {
     float4 y = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
@@ -72,6 +77,7 @@ __device__ __forceinline__ void epilogue_store(float4 acc, int row, int off, con
         y.w = tanhf(y.w);
     }
     *reinterpret_cast<float4 *>(Y + o) = y;
+    return (y.x != 0.f) | (y.y != 0.f) | (y.z != 0.f) | (y.w != 0.f);
 }
 
 template <int D, int ACT>
@@ -311,7 +317,7 @@ spmm_bulk_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__re
 // per-row bookkeeping of the warp-per-segment kernel (D = 64: 8 lanes x 2 float4, four rows per warp),
 // and the shuffle / address / predicate work of a step is shared by 4 nonzeros.  Groups of one warp take
 // adjacent segments of the length-sorted plan, so their trip counts match.
-template <int D, int LPR, int U, int ACT, bool SPLIT>
+template <int D, int LPR, int U, int ACT, bool SPLIT, bool MASKED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
                   const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
@@ -344,6 +350,7 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
         if (lg < cnt) {
             c = __ldg(cp + base + lg);
             v = __ldg(vp + base + lg);
+            if (MASKED && sp.x_mask[c] == 0) c = -1;      // source row is all zeros: nothing to gather
         }
         const int lim = min(LPR, maxlen - base);
         for (int j = 0; j < lim; j += U) {
@@ -355,7 +362,7 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
                 const int cj = __shfl_sync(0xffffffffu, c, e, LPR);
                 vv[u] = __shfl_sync(0xffffffffu, v, e, LPR);
                 const float *xr = ((!SPLIT || cj < sp.x_split) ? Xo : X1o) + (size_t)cj * D;
-                if (e < cnt) {
+                if (e < cnt && (!MASKED || cj >= 0)) {
 #pragma unroll
                     for (int t = 0; t < VPL; ++t) x[u][t] = fr::ldg_f4(xr + 4 * LPR * t);
                 } else {
@@ -371,15 +378,20 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
         }
     }
     if (s.w == -2) return;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
     if (s.w < 0) {
+        bool nz = false;
 #pragma unroll
         for (int t = 0; t < VPL; ++t)
-            epilogue_store<D, ACT>(acc[t], s.x, 4 * (lg + LPR * t), (Z != nullptr && s.x >= sp.z_split) ? sp.Z1_adj : Z, alpha,
-                                   beta, bias, Y);
+            nz |= epilogue_store<D, ACT>(acc[t], s.x, 4 * (lg + LPR * t), (Z != nullptr && s.x >= sp.z_split) ? sp.Z1_adj : Z,
+                                         alpha, beta, bias, Y);
+        if (sp.y_mask != nullptr) {
+            nz = __any_sync(gmask, nz);
+            if (lg == 0) sp.y_mask[s.x] = nz ? 1 : 0;
+        }
         return;
     }
     // ---- long row: publish this segment's partial; the last segment to arrive folds all in fixed order
-    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
     const int4 lr = __ldg(long_rows + s.w);              // first_seg, n_parts, part_base, row
     const int part = (int)(sidx - lr.x);
 #pragma unroll
@@ -392,6 +404,7 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
     ticket = __shfl_sync(gmask, ticket, g * LPR);
     if (ticket != lr.y - 1) return;
     __threadfence();
+    bool nz_long = false;
 #pragma unroll
     for (int t = 0; t < VPL; ++t) {
         float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -405,8 +418,12 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
             for (int u = 0; u < 8; ++u) fr::add4(tot, p8[u]);
         }
         for (; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(pp + (size_t)k * D));
-        epilogue_store<D, ACT>(tot, lr.w, 4 * (lg + LPR * t), (Z != nullptr && lr.w >= sp.z_split) ? sp.Z1_adj : Z, alpha, beta,
-                               bias, Y);
+        nz_long |= epilogue_store<D, ACT>(tot, lr.w, 4 * (lg + LPR * t), (Z != nullptr && lr.w >= sp.z_split) ? sp.Z1_adj : Z,
+                                          alpha, beta, bias, Y);
+    }
+    if (sp.y_mask != nullptr) {
+        nz_long = __any_sync(gmask, nz_long);
+        if (lg == 0) sp.y_mask[lr.w] = nz_long ? 1 : 0;
     }
     if (lg == 0) counters[s.w] = 0;
 }
@@ -424,10 +441,13 @@ int launch_group_shape(const int4 *seg, int64_t n_seg, const int4 *lrows, const 
     }
     fr::LaunchTimer _lt("spmm_group_kernel", st);
     if (sp.x_split != 0x7fffffff)   // two-segment gather only where it is used (first layer of a forward)
-        spmm_group_kernel<D, LPR, U, ACT, true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+        spmm_group_kernel<D, LPR, U, ACT, true, false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+            seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
+    else if (sp.x_mask != nullptr)  // masked gather only in the backward launches that carry a row mask
+        spmm_group_kernel<D, LPR, U, ACT, false, true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
             seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
     else
-        spmm_group_kernel<D, LPR, U, ACT, false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+        spmm_group_kernel<D, LPR, U, ACT, false, false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
             seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
     return fr::check_launch("fr_spmm_csr_f32(group)");
 }
@@ -497,8 +517,8 @@ int launch(const int4 *seg, int64_t n_seg, const int4 *lrows, const int *col, co
         if (act == 0) return launch_group<D, 0>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st, sp);
         return launch_group<D, 1>(seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, st, sp);
     }
-    if (sp.x_split != 0x7fffffff || sp.z_split != 0x7fffffff) {
-        fr::set_error("fr_spmm_csr_f32_split: two-segment operands need the default (group) kernel");
+    if (sp.x_split != 0x7fffffff || sp.z_split != 0x7fffffff || sp.x_mask != nullptr || sp.y_mask != nullptr) {
+        fr::set_error("fr_spmm_csr_f32_split: two-segment operands / row masks need the default (group) kernel");
         return FR_EUNSUPPORTED;
     }
     if (spmm_impl() == 1) {
@@ -598,11 +618,11 @@ extern "C" int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, in
     return FR_OK;
 }
 
-extern "C" int fr_spmm_csr_f32_split(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
-                                     const int32_t *col_idx, const float *val, int32_t d, const float *X0, const float *X1,
-                                     int32_t x_split, const float *Z0, const float *Z1, int32_t z_split, float alpha,
-                                     float beta, const float *bias, int32_t act, float *Y, float *partial,
-                                     int32_t *counters, void *stream) {
+static int spmm_entry(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                      const int32_t *col_idx, const float *val, int32_t d, const float *X0, const float *X1,
+                      int32_t x_split, const float *Z0, const float *Z1, int32_t z_split, float alpha,
+                      float beta, const float *bias, int32_t act, float *Y, float *partial,
+                      int32_t *counters, const uint8_t *x_mask, uint8_t *y_mask, void *stream) {
     FR_REQUIRE(n_seg >= 0 && n_long >= 0, "fr_spmm_csr_f32: negative extent");
     if (n_seg == 0) return FR_OK;
     FR_REQUIRE(seg && X0 && Y, "fr_spmm_csr_f32: null seg/X/Y");
@@ -619,6 +639,9 @@ extern "C" int fr_spmm_csr_f32_split(const int32_t *seg, int64_t n_seg, const in
     sp.X1_adj = X1 ? X1 - (size_t)x_split * d : X0;
     sp.z_split = Z1 ? z_split : 0x7fffffff;
     sp.Z1_adj = Z1 ? Z1 - (size_t)z_split * d : Z0;
+    FR_REQUIRE(x_mask == nullptr || X1 == nullptr, "fr_spmm_csr_f32_masked: a row mask needs a single-table X");
+    sp.x_mask = x_mask;
+    sp.y_mask = y_mask;
     cudaStream_t st = (cudaStream_t)stream;
     const int4 *sg = reinterpret_cast<const int4 *>(seg);
     const int4 *lr = reinterpret_cast<const int4 *>(long_rows);
@@ -630,6 +653,23 @@ extern "C" int fr_spmm_csr_f32_split(const int32_t *seg, int64_t n_seg, const in
             fr::set_error("fr_spmm_csr_f32: d=%d unsupported (32, 64, 128)", d);
             return FR_EUNSUPPORTED;
     }
+}
+
+extern "C" int fr_spmm_csr_f32_split(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                                     const int32_t *col_idx, const float *val, int32_t d, const float *X0, const float *X1,
+                                     int32_t x_split, const float *Z0, const float *Z1, int32_t z_split, float alpha,
+                                     float beta, const float *bias, int32_t act, float *Y, float *partial,
+                                     int32_t *counters, void *stream) {
+    return spmm_entry(seg, n_seg, long_rows, n_long, col_idx, val, d, X0, X1, x_split, Z0, Z1, z_split, alpha, beta, bias, act,
+                      Y, partial, counters, nullptr, nullptr, stream);
+}
+
+extern "C" int fr_spmm_csr_f32_masked(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                                      const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z,
+                                      float alpha, float beta, float *Y, float *partial, int32_t *counters,
+                                      const uint8_t *x_mask, uint8_t *y_mask, void *stream) {
+    return spmm_entry(seg, n_seg, long_rows, n_long, col_idx, val, d, X, nullptr, 0, Z, nullptr, 0, alpha, beta, nullptr, 0, Y,
+                      partial, counters, x_mask, y_mask, stream);
 }
 
 extern "C" int fr_spmm_csr_f32(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,

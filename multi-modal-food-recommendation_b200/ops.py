@@ -31,6 +31,61 @@ def _idx(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous() if t.dtype == torch.int64 else t.to(torch.int64).contiguous()
 
 
+# ------------------------------------------------------------------------------ row-activity masks
+# The gradient of a mini-batch loss w.r.t. a propagated table is exactly zero outside the rows the batch
+# touched, and stays sparse through the first backward propagation layers.  Producers of such gradients
+# (`rank_loss`, `item_views`, the masked propagation itself) register a uint8 row mask for the gradient tensor
+# they hand to autograd; the propagation backward looks its upstream gradient up here and, on a hit, skips
+# the gathers of all-zero rows (results are bit-identical).  An entry keeps a reference to its tensor, so a
+# data pointer found here cannot have been recycled for another tensor; entries are popped when consumed and
+# the registry is cleared at the start of every backward pass of `rank_loss`.
+_ROW_MASKS = {}
+USE_ROW_MASKS = True
+
+
+def _register_mask(t: torch.Tensor, mask: torch.Tensor):
+    if USE_ROW_MASKS:
+        _ROW_MASKS[(t.data_ptr(), tuple(t.shape))] = (t, mask)
+
+
+def _take_mask(t: torch.Tensor):
+    hit = _ROW_MASKS.pop((t.data_ptr(), tuple(t.shape)), None)
+    return None if hit is None else hit[1]
+
+
+def spmm_masked(graph: PropGraph, X, Z, alpha, beta, x_mask, want_mask: bool):
+    """Backward-pass launch: `alpha * S @ X + beta * Z` skipping rows of X whose mask byte is 0; optionally
+    returns the row mask of the result."""
+    d = X.shape[1]
+    out = torch.empty((graph.n_rows, d), dtype=torch.float32, device=X.device)
+    y_mask = torch.empty(graph.n_rows, dtype=torch.uint8, device=X.device) if want_mask else None
+    prof = PROFILE
+    if prof is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _lib.check(_L.fr_spmm_csr_f32_masked(
+        graph.seg.data_ptr(), graph.n_seg, graph.long_rows.data_ptr(), graph.n_long, graph.col.data_ptr(),
+        graph.val.data_ptr(), d, X.data_ptr(), _lib.ptr(Z), float(alpha), float(beta), out.data_ptr(),
+        graph.partial(d).data_ptr(), graph.counters.data_ptr(), x_mask.data_ptr(), _lib.ptr(y_mask),
+        _lib.stream_ptr()), "fr_spmm_csr_f32_masked")
+    if prof is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        prof.append((ev0, ev1, graph.spmm_bytes(d), graph, Z is not None))
+    return out, y_mask
+
+
+def propagate_mean_masked(graph: PropGraph, g: torch.Tensor, n_layers: int, mask: torch.Tensor):
+    """`mean_l S^l g` for an upstream gradient `g` with row mask `mask` (Horner form; every layer's input is
+    `previous + g`, whose mask is the previous layer's output mask).  Returns (result, its row mask)."""
+    inv = 1.0 / (n_layers + 1)
+    t, m = g, mask
+    for layer in range(n_layers):
+        last = layer == n_layers - 1
+        t, m = spmm_masked(graph, t, g, inv if last else 1.0, inv if last else 1.0, m, want_mask=True)
+    return t, m
+
+
 # ------------------------------------------------------------------------------------ propagation
 def spmm(graph: PropGraph, X: torch.Tensor, Z: torch.Tensor | None = None, alpha: float = 1.0, beta: float = 0.0,
          bias: torch.Tensor | None = None, act: int = 0, out: torch.Tensor | None = None,
@@ -91,7 +146,13 @@ class _PropagateMean(torch.autograd.Function):
         gt = ctx.graph.T
         if gt is None:
             raise _lib.FoodRecError("graph has no transpose plan; build it with a `.T`")
-        return propagate_mean_raw(gt, g.contiguous(), ctx.n_layers), None, None
+        g = g.contiguous()
+        mask = _take_mask(g) if ctx.n_layers > 0 else None
+        if mask is not None:
+            r, rm = propagate_mean_masked(gt, g, ctx.n_layers, mask)
+            _register_mask(r, rm)
+            return r, None, None
+        return propagate_mean_raw(gt, g, ctx.n_layers), None, None
 
 
 class _PropagateMean2(torch.autograd.Function):
@@ -108,7 +169,15 @@ class _PropagateMean2(torch.autograd.Function):
         gt = ctx.graph.T
         if gt is None:
             raise _lib.FoodRecError("graph has no transpose plan; build it with a `.T`")
-        r = propagate_mean_raw(gt, g.contiguous(), ctx.n_layers)
+        g = g.contiguous()
+        mask = _take_mask(g) if ctx.n_layers > 0 else None
+        if mask is not None:
+            r, rm = propagate_mean_masked(gt, g, ctx.n_layers, mask)
+            top, bottom = r[:ctx.n_top], r[ctx.n_top:]
+            _register_mask(top, rm[:ctx.n_top])
+            _register_mask(bottom, rm[ctx.n_top:])
+            return top, bottom, None, None
+        r = propagate_mean_raw(gt, g, ctx.n_layers)
         return r[:ctx.n_top], r[ctx.n_top:], None, None
 
 
@@ -197,7 +266,12 @@ class _RankLoss(torch.autograd.Function):
             if ctx.needs_input_grad[9 + k] and t.data_ptr() not in keys:
                 keys.append(t.data_ptr())
                 shapes.append(t.shape)
-        flat = torch.zeros(sum(sh[0] * sh[1] for sh in shapes), dtype=torch.float32, device=emb.device)
+        _ROW_MASKS.clear()   # a new backward pass starts here: nothing registered earlier may be used again
+        n_flat = sum(sh[0] * sh[1] for sh in shapes)
+        want_mask = USE_ROW_MASKS and ctx.needs_input_grad[0]
+        n_mask_words = (emb.shape[0] + 3) // 4 if want_mask else 0     # the row mask shares the zero fill
+        flat = torch.zeros(n_flat + n_mask_words, dtype=torch.float32, device=emb.device)
+        emb_mask = flat[n_flat:].view(torch.uint8)[:emb.shape[0]] if want_mask else None
         views, o = [], 0
         for sh in shapes:
             views.append(flat[o:o + sh[0] * sh[1]].view(sh[0], sh[1]))
@@ -210,7 +284,9 @@ class _RankLoss(torch.autograd.Function):
         _lib.check(_L.fr_rank_loss_bwd(
             emb.data_ptr(), d, item_off, u.data_ptr(), p.data_ptr(), n.data_ptr(), B, coef.data_ptr(),
             g_out.data_ptr(), _lib.ptr(d_emb), ng, _ptr_array(reg_tabs), _ptr_array(reg_idx), cnt, pad, reg_den,
-            gnorm.data_ptr(), _ptr_array(d_tabs), _lib.stream_ptr()), "fr_rank_loss_bwd")
+            gnorm.data_ptr(), _ptr_array(d_tabs), _lib.ptr(emb_mask), _lib.stream_ptr()), "fr_rank_loss_bwd")
+        if emb_mask is not None:
+            _register_mask(d_emb, emb_mask)
         # a table shared by several groups gets its (already summed) gradient once
         seen, grads = set(), []
         for k, t in enumerate(reg_tabs):
@@ -306,14 +382,15 @@ def _dcor_forward(tabs, idx, pairs, scale):
     return out, (Dm, rowmean, dfds, gm)
 
 
-def _dcor_backward(tabs, idx, pairs, state, g_terms, d_tabs):
-    """Accumulates sum_p g_terms[p] * d term_p / d tab_v into the dense `d_tabs[v]` (None = skip)."""
+def _dcor_backward(tabs, idx, pairs, state, g_terms, d_tabs, masks=None):
+    """Accumulates sum_p g_terms[p] * d term_p / d tab_v into the dense `d_tabs[v]` (None = skip); `masks[v]`
+    (uint8 per row, optional) get the touched rows marked."""
     Dm, rowmean, dfds, gm = state
     V, P, n, d = len(tabs), len(pairs), idx.numel(), tabs[0].shape[1]
     pr = (C.c_int32 * (2 * P))(*[x for ab in pairs for x in ab])
     _lib.check(_L.fr_dcor_bwd(_ptr_array(tabs), V, d, idx.data_ptr(), n, pr, P, Dm.data_ptr(), rowmean.data_ptr(),
                               dfds.data_ptr(), gm.data_ptr(), g_terms.data_ptr(), _ptr_array(d_tabs),
-                              _lib.stream_ptr()), "fr_dcor_bwd")
+                              _ptr_array(masks) if masks is not None else None, _lib.stream_ptr()), "fr_dcor_bwd")
 
 
 def _term_grads(g_terms, g_total, P):
@@ -363,6 +440,7 @@ class _GradHolder:
 
     def __init__(self):
         self.d_tabs = None
+        self.masks = None
         self.stream = None
         self.done = False
         self.consumed = False
@@ -383,10 +461,13 @@ class _DcorTotalInto(torch.autograd.Function):
         state, tabs = ctx.saved_tensors[1:5], ctx.saved_tensors[5:]
         h = ctx.holder
         d_tabs = [torch.zeros_like(t) for t in tabs]
-        _dcor_backward(tabs, idx, ctx.pairs, state, _term_grads(None, g_total, len(ctx.pairs)), d_tabs)
+        masks = None
+        if USE_ROW_MASKS and not h.consumed:
+            masks = [torch.zeros(t.shape[0], dtype=torch.uint8, device=t.device) for t in tabs]
+        _dcor_backward(tabs, idx, ctx.pairs, state, _term_grads(None, g_total, len(ctx.pairs)), d_tabs, masks)
         if h.consumed:                       # the other half already ran: ordinary gradients, autograd adds them
             return (None, None, None, None, *d_tabs)
-        h.d_tabs, h.stream, h.done = d_tabs, torch.cuda.current_stream(), True
+        h.d_tabs, h.masks, h.stream, h.done = d_tabs, masks, torch.cuda.current_stream(), True
         return (None, None, None, None) + (None,) * len(tabs)
 
 
@@ -408,18 +489,25 @@ class _SumRowsInto(torch.autograd.Function):
         h, d = ctx.holder, ctx.shapes[0][1]
         g_item = g_item.contiguous()
         rows = (C.c_int64 * len(ctx.shapes))(*[int(sh[0]) for sh in ctx.shapes])
+        src_mask = _take_mask(g_item)
         if h.done and not h.consumed:        # add to the parked contrastive gradients (other stream: join first)
             cur = torch.cuda.current_stream()
             if h.stream is not None and h.stream != cur:
                 cur.wait_stream(h.stream)
-                for t in h.d_tabs:
+                for t in h.d_tabs + (h.masks or []):
                     t.record_stream(cur)
-            d_tabs, acc = h.d_tabs, 1
+            d_tabs, masks, acc = h.d_tabs, h.masks, 1
         else:
             d_tabs, acc = [torch.empty(sh, dtype=torch.float32, device=ctx.dev) for sh in ctx.shapes], 0
+            masks = ([torch.empty(sh[0], dtype=torch.uint8, device=ctx.dev) for sh in ctx.shapes]
+                     if (USE_ROW_MASKS and src_mask is not None) else None)
         h.consumed = True
         _lib.check(_L.fr_spread_rows(g_item.data_ptr(), d, ctx.n_items, _ptr_array(d_tabs), rows, len(d_tabs), acc,
+                                     _lib.ptr(src_mask), _ptr_array(masks) if masks is not None else None,
                                      _lib.stream_ptr()), "fr_spread_rows")
+        if masks is not None:
+            for t, m in zip(d_tabs, masks):
+                _register_mask(t, m)
         return (None, None, *d_tabs)
 
 

@@ -144,3 +144,51 @@ def test_propgraph_from_reference_style_sparse_tensor(mini_ds):
     assert torch.equal(g.col, g0.col) and torch.equal(g.val, g0.val)
     X = torch.randn(S.shape[0], 64)
     close(ops.spmm(g, X.cuda()), torch.sparse.mm(S, X))
+
+
+@pytest.mark.parametrize("layers", [1, 2, 3])
+def test_masked_backward_propagation_is_bit_identical(layers):
+    """Skipping the gathers of all-zero gradient rows (row-activity masks) must not change a single bit, and the
+    mask the kernel emits for its output must cover every nonzero row."""
+    from foodrec_b200 import graph as G, ops
+    from foodrec_b200.synth import make_dataset
+    ds = make_dataset("C1", features=False)
+    g = G.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items, "cuda")
+    N = g.n_rows
+    torch.manual_seed(layers)
+    grad = torch.zeros(N, 64, device="cuda")
+    rows = torch.randint(0, N, (1500,), device="cuda")
+    grad[rows] = torch.randn(1500, 64, device="cuda")
+    mask = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    mask[rows] = 1
+    dense = ops.propagate_mean_raw(g, grad, layers)
+    sparse, out_mask = ops.propagate_mean_masked(g, grad, layers, mask)
+    assert torch.equal(dense, sparse)
+    nz = (dense != 0).any(dim=1)
+    assert bool((out_mask.bool() | ~nz).all())          # every nonzero row is marked active
+    # a conservative (all-ones) mask is also exact
+    sparse2, _ = ops.propagate_mean_masked(g, grad, layers, torch.ones(N, dtype=torch.uint8, device="cuda"))
+    assert torch.equal(dense, sparse2)
+
+
+def test_row_masks_do_not_change_model_gradients(mini_ds, mini_batches):
+    """CLUSSL loss + backward with and without the row-mask fast path: same losses, gradients equal up to the
+    order of fp32 atomics in the loss kernels."""
+    from foodrec_b200 import ops
+    from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
+    from test_gpu_clussl import cfg_for, dev_batch
+    torch.manual_seed(999)
+    m = PRICAI_ModelX(cfg_for(mini_ds), mini_ds).to("cuda")
+    grads = {}
+    for flag in (True, False):
+        ops.USE_ROW_MASKS = flag
+        try:
+            m.zero_grad()
+            losses = m.calculate_loss(dev_batch(mini_batches[0]))
+            sum(losses).backward()
+            grads[flag] = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+        finally:
+            ops.USE_ROW_MASKS = True
+    for n in grads[True]:
+        a, b = grads[True][n], grads[False][n]
+        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max()) + 1e-12, n

@@ -3,7 +3,7 @@ PKG   := multi-modal-food-recommendation_b200
 CSRC  := $(PKG)/csrc
 NVCC  ?= /usr/local/cuda/bin/nvcc
 ARCH  := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Iinclude -I$(CSRC) --expt-relaxed-constexpr
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Iinclude -I$(CSRC) --expt-relaxed-constexpr $(EXTRA)
 SRCS  := $(wildcard $(CSRC)/*.cu)
 OBJS  := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 LIB   := $(PKG)/libfoodrec_b200.so

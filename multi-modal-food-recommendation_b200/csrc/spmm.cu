@@ -18,6 +18,9 @@
 namespace {
 
 constexpr int kWarpsPerBlock = 8;
+#ifndef FR_GROUP_MIN_BLOCKS
+#define FR_GROUP_MIN_BLOCKS 4
+#endif
 
 // Optional two-segment operands: rows [0, split) come from the primary pointer, rows >= split from a second
 // table (`*_adj` = second pointer - split * D, so both are indexed by the global row).  This is how the
@@ -318,7 +321,7 @@ spmm_bulk_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__re
 // and the shuffle / address / predicate work of a step is shared by 4 nonzeros.  Groups of one warp take
 // adjacent segments of the length-sorted plan, so their trip counts match.
 template <int D, int LPR, int U, int ACT, bool SPLIT, bool MASKED>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, FR_GROUP_MIN_BLOCKS)
 spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
                   const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
                   const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,

@@ -195,6 +195,20 @@ int fr_rescore_topk_f32(const float *A, const int64_t *a_rows, const float *B, i
                         const float *bias, int32_t metric /* 0: scale*a.b+bias, 1: -|a-b|^2 */, const int32_t *cand,
                         int32_t kc, int32_t M, int32_t k, float *out_val, int64_t *out_idx, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SimCLR NT-Xent ("InfoNCE") over the two halves of hidden [2b, d] (d in {32, 64}).
+ * Replaces `PRICAI_ModelX.CL_loss` (FoodRec/models/pricai_modelx.py:354-378; dormant in the reference, its
+ * call is commented out at :259): cosine-normalise (optional), logits / temperature, diagonal of the aa / bb
+ * blocks masked, two cross-entropies, (loss_a + loss_b) / b.  Equivalent single-Gram form:
+ *   out[0] = sum_r [ logsumexp_{c != r} G[r, c] - G[r, pair(r)] ] / b^2,  G = Hn Hn^T / temperature.
+ * State for the backward (caller-allocated): hn [2b, d], norm [2b], G [2b, 2b], lse [2b];
+ * ws: fr_infonce_ws_floats(2b) floats of scratch.  d_hidden [2b, d] is written (not accumulated). */
+int64_t fr_infonce_ws_floats(int32_t n);
+int fr_infonce_fwd(const float *hidden, int32_t b, int32_t d, float temperature, int32_t normalise, float *hn,
+                   float *norm, float *G, float *lse, float *out, float *ws, void *stream);
+int fr_infonce_bwd(const float *hn, const float *norm, const float *G, const float *lse, int32_t b, int32_t d,
+                   float temperature, int32_t normalise, const float *g_out, float *d_hidden, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

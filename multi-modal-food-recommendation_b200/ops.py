@@ -537,7 +537,39 @@ def correlation_distance(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return dcor_terms([x, y], idx, [(0, 1)])
 
 
+class _InfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, temperature, hidden_norm):
+        _chk_f32(hidden, "hidden")
+        b, d = hidden.shape[0] // 2, hidden.shape[1]
+        n, dev = 2 * b, hidden.device
+        hn = torch.empty((n, d), dtype=torch.float32, device=dev)
+        norm = torch.empty(n, dtype=torch.float32, device=dev)
+        G = torch.empty((n, n), dtype=torch.float32, device=dev)
+        lse = torch.empty(n, dtype=torch.float32, device=dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(_L.fr_infonce_ws_floats(n)), dtype=torch.float32, device=dev)
+        _lib.check(_L.fr_infonce_fwd(hidden.data_ptr(), b, d, float(temperature), int(bool(hidden_norm)), hn.data_ptr(),
+                                     norm.data_ptr(), G.data_ptr(), lse.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                     _lib.stream_ptr()), "fr_infonce_fwd")
+        ctx.save_for_backward(hn, norm, G, lse)
+        ctx.meta = (b, d, float(temperature), int(bool(hidden_norm)), hidden.shape[0])
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        hn, norm, G, lse = ctx.saved_tensors
+        b, d, tau, nrm, rows = ctx.meta
+        g = g.to(torch.float32).reshape(1).contiguous()
+        dh = torch.empty((rows, d), dtype=torch.float32, device=hn.device)
+        if rows > 2 * b:
+            dh[2 * b:].zero_()          # an odd trailing row takes no part (hidden.shape[0] // 2 in the reference)
+        _lib.check(_L.fr_infonce_bwd(hn.data_ptr(), norm.data_ptr(), G.data_ptr(), lse.data_ptr(), b, d, tau, nrm,
+                                     g.data_ptr(), dh.data_ptr(), _lib.stream_ptr()), "fr_infonce_bwd")
+        return dh, None, None
+
+
 def info_nce(hidden: torch.Tensor, temperature: float = 0.5, hidden_norm: bool = True) -> torch.Tensor:
-    """SimCLR NT-Xent over the two halves of `hidden` (`CL_loss`, pricai_modelx.py:354-378)."""
-    from . import contrastive
-    return contrastive.info_nce(hidden, temperature, hidden_norm)
+    """SimCLR NT-Xent over the two halves of `hidden` (`CL_loss`, pricai_modelx.py:354-378): three fused
+    launches forward, one backward (one symmetric Gram matrix instead of four logit blocks)."""
+    return _InfoNCE.apply(hidden.contiguous(), float(temperature), bool(hidden_norm))

@@ -118,3 +118,20 @@ def test_info_nce_golden():
     c.backward()
     close(c, g["nce/out"])
     close(h.grad, g["nce/gh"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("rows,temperature,norm", [(1024, 0.5, True), (130, 0.2, True), (257, 0.5, False)])
+def test_info_nce_vs_oracle(rows, temperature, norm):
+    """Fused NT-Xent (one Gram matrix) vs the reference's four-block formulation restated in the oracle,
+    including an odd trailing row (ignored, zero gradient) and the un-normalised variant."""
+    from foodrec_b200 import ops
+    from oracle import losses
+    torch.manual_seed(rows)
+    h = (torch.randn(rows, 64) * (1.0 if norm else 0.3)).requires_grad_(True)
+    ref = losses.info_nce(h, temperature=temperature, hidden_norm=norm)
+    ref.backward()
+    hd = h.detach().cuda().requires_grad_(True)
+    out = ops.info_nce(hd, temperature=temperature, hidden_norm=norm)
+    out.backward()
+    close(out, ref.detach().numpy())
+    close(hd.grad, h.grad.numpy(), rtol=2e-5)

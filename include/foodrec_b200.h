@@ -195,6 +195,15 @@ int fr_rescore_topk_f32(const float *A, const int64_t *a_rows, const float *B, i
                         const float *bias, int32_t metric /* 0: scale*a.b+bias, 1: -|a-b|^2 */, const int32_t *cand,
                         int32_t kc, int32_t M, int32_t k, float *out_val, int64_t *out_idx, void *stream);
 
+/* Mean cosine similarity of dense rows A[i] with gathered rows T[idx[i]] (eps = 1e-8 on each norm):
+ * HealthRec's knowledge-distillation term `1 - cosine_similarity(item_know, cat(pos_e, neg_e)).mean()`
+ * (FoodRec/models/cikm_model.py:263-264).  cosv / na / nt [n] keep the per-row state for the backward, which
+ * writes dA [n, d] (or NULL) and scatter-adds into the dense dT (or NULL). */
+int fr_cosine_mean_fwd(const float *A, const float *T, const int64_t *idx, int64_t n, int32_t d, float *out, float *cosv,
+                       float *na, float *nt, void *stream);
+int fr_cosine_mean_bwd(const float *A, const float *T, const int64_t *idx, int64_t n, int32_t d, const float *cosv,
+                       const float *na, const float *nt, const float *g_out, float *dA, float *dT, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * SimCLR NT-Xent ("InfoNCE") over the two halves of hidden [2b, d] (d in {32, 64}).
  * Replaces `PRICAI_ModelX.CL_loss` (FoodRec/models/pricai_modelx.py:354-378; dormant in the reference, its

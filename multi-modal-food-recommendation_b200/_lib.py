@@ -54,6 +54,8 @@ SIGNATURES = {
     "fr_gemm_topk_bf16": (C.c_int, [_p, _i32, _p, _i32, _i32, _f32, _p, _p, _p, _p, _i32, _p, _p, _p, _i64, _p]),
     "fr_rescore_topk_f32": (C.c_int, [_p, _p, _p, _i32, _f32, _p, _i32, _p, _i32, _i32, _i32, _p, _p, _p]),
     "fr_csr_from_coo": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "fr_cosine_mean_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "fr_cosine_mean_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "fr_infonce_ws_floats": (_i64, [_i32]),
     "fr_infonce_fwd": (C.c_int, [_p, _i32, _i32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "fr_infonce_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _f32, _i32, _p, _p, _p]),

@@ -206,3 +206,85 @@ extern "C" int fr_spread_rows(const float *g, int32_t d, int64_t rows, float *co
     spread_rows_kernel<<<dim3(grid1d(mx, 256), n_tabs), 256, 0, (cudaStream_t)stream>>>(t, rows * (d / 4), g, accumulate, src_mask, d / 4);
     return fr::check_launch("fr_spread_rows");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Mean cosine similarity between dense rows A[i] and gathered rows T[idx[i]] -- HealthRec's knowledge-
+// distillation term `1 - cosine_similarity(item_know, cat(pos_e, neg_e)).mean()`
+// (FoodRec/models/cikm_model.py:263-264,304-308) without materialising the gathered rows.
+// cos = a.t / (max(|a|, eps) max(|t|, eps)), eps = 1e-8 (torch.nn.functional.cosine_similarity).
+namespace {
+__global__ void cosine_mean_fwd_kernel(const float *__restrict__ A, const float *__restrict__ T, const int64_t *__restrict__ idx,
+                                       long long n, int d, float *__restrict__ cosv, float *__restrict__ na, float *__restrict__ nt) {
+    const int lane = threadIdx.x & 31;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const float *a = A + (size_t)i * d, *t = T + (size_t)idx[i] * d;
+    float dot = 0.f, sa = 0.f, st = 0.f;
+    for (int k = lane; k < d; k += 32) {
+        const float x = a[k], y = __ldg(t + k);
+        dot = fmaf(x, y, dot);
+        sa = fmaf(x, x, sa);
+        st = fmaf(y, y, st);
+    }
+    dot = fr::warp_sum(dot);
+    sa = fr::warp_sum(sa);
+    st = fr::warp_sum(st);
+    if (lane == 0) {
+        const float x = fmaxf(sqrtf(sa), 1e-8f), y = fmaxf(sqrtf(st), 1e-8f);
+        na[i] = x;
+        nt[i] = y;
+        cosv[i] = dot / (x * y);
+    }
+}
+__global__ void mean_kernel(const float *__restrict__ v, long long n, float *__restrict__ out) {   // one block, fixed order
+    __shared__ float red[32];
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    s = fr::warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        out[0] = t / (float)n;
+    }
+}
+__global__ void cosine_mean_bwd_kernel(const float *__restrict__ A, const float *__restrict__ T, const int64_t *__restrict__ idx,
+                                       long long n, int d, const float *__restrict__ cosv, const float *__restrict__ na,
+                                       const float *__restrict__ nt, const float *__restrict__ g_out, float *__restrict__ dA,
+                                       float *__restrict__ dT) {
+    const int lane = threadIdx.x & 31;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const size_t ao = (size_t)i * d, to = (size_t)idx[i] * d;
+    const float g = __ldg(g_out) / (float)n, c = cosv[i], x = na[i], y = nt[i];
+    const bool ax = x > 1e-8f, ty = y > 1e-8f;      // clamped norms carry no gradient through the norm
+    for (int k = lane; k < d; k += 32) {
+        const float a = A[ao + k], t = __ldg(T + to + k);
+        if (dA != nullptr) dA[ao + k] = g * (t / (x * y) - (ax ? c * a / (x * x) : 0.f));
+        if (dT != nullptr) atomicAdd(dT + to + k, g * (a / (x * y) - (ty ? c * t / (y * y) : 0.f)));
+    }
+}
+}  // namespace
+
+extern "C" int fr_cosine_mean_fwd(const float *A, const float *T, const int64_t *idx, int64_t n, int32_t d, float *out,
+                                  float *cosv, float *na, float *nt, void *stream) {
+    FR_REQUIRE(A && T && idx && out && cosv && na && nt && n > 0 && d > 0, "fr_cosine_mean_fwd: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        fr::LaunchTimer _lt("cosine_mean_fwd_kernel", st);
+        cosine_mean_fwd_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(A, T, idx, n, d, cosv, na, nt);
+    }
+    if (int rc = fr::check_launch("fr_cosine_mean_fwd")) return rc;
+    mean_kernel<<<1, 1024, 0, st>>>(cosv, n, out);
+    return fr::check_launch("fr_cosine_mean_fwd/mean");
+}
+
+extern "C" int fr_cosine_mean_bwd(const float *A, const float *T, const int64_t *idx, int64_t n, int32_t d, const float *cosv,
+                                  const float *na, const float *nt, const float *g_out, float *dA, float *dT, void *stream) {
+    FR_REQUIRE(A && T && idx && cosv && na && nt && g_out && n > 0 && d > 0, "fr_cosine_mean_bwd: bad argument");
+    fr::LaunchTimer _lt("cosine_mean_bwd_kernel", (cudaStream_t)stream);
+    cosine_mean_bwd_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A, T, idx, n, d, cosv, na, nt,
+                                                                                              g_out, dA, dT);
+    return fr::check_launch("fr_cosine_mean_bwd");
+}

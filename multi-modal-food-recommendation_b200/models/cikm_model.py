@@ -149,8 +149,8 @@ class CIKM_Model(DotProductRecommender):
         mf_loss, reg = ops.rank_loss(all_emb, self.n_users, user, pos_item, neg_item,
                                      [(uw, user), (iw, pos_item), (iw, neg_item), (gw, pos_ing, pad), (gw, neg_ing, pad)],
                                      reg_den=float(neg_ing.shape[0]), gamma=self.mf_loss.gamma)
-        item_rows = ops.gather_rows(all_emb, all_item + self.n_users)
-        kd = 1 - F.cosine_similarity(item_know, item_rows, dim=-1).mean()
+        # 1 - mean cos(item_know, [pos_e; neg_e]) against the propagated item rows, gathered inside the kernel
+        kd = 1 - ops.cosine_mean(item_know, all_emb, all_item + self.n_users)
         kd_loss = torch.clamp_min(kd - self.kd_threshold, 0.0)
         return mf_loss, self.loss_health * health_loss, self.loss_kd * kd_loss, (self.reg_weight * reg).reshape(1)
 

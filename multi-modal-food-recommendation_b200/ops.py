@@ -336,6 +336,39 @@ def gather_rows(tab: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return _GatherRows.apply(tab.contiguous(), _idx(idx, "idx"))
 
 
+class _CosineMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, T, idx):
+        _chk_f32(A, "A")
+        _chk_f32(T, "table")
+        n, d, dev = A.shape[0], A.shape[1], A.device
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        state = torch.empty((3, n), dtype=torch.float32, device=dev)
+        _lib.check(_L.fr_cosine_mean_fwd(A.data_ptr(), T.data_ptr(), idx.data_ptr(), n, d, out.data_ptr(),
+                                         state[0].data_ptr(), state[1].data_ptr(), state[2].data_ptr(), _lib.stream_ptr()),
+                   "fr_cosine_mean_fwd")
+        ctx.save_for_backward(A, T, idx, state)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        A, T, idx, state = ctx.saved_tensors
+        n, d = A.shape
+        g = g.to(torch.float32).reshape(1).contiguous()
+        dA = torch.empty_like(A) if ctx.needs_input_grad[0] else None
+        dT = torch.zeros_like(T) if ctx.needs_input_grad[1] else None
+        _lib.check(_L.fr_cosine_mean_bwd(A.data_ptr(), T.data_ptr(), idx.data_ptr(), n, d, state[0].data_ptr(),
+                                         state[1].data_ptr(), state[2].data_ptr(), g.data_ptr(), _lib.ptr(dA), _lib.ptr(dT),
+                                         _lib.stream_ptr()), "fr_cosine_mean_bwd")
+        return dA, dT, None
+
+
+def cosine_mean(A: torch.Tensor, table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """`cosine_similarity(A, table[idx], dim=-1).mean()` without materialising the gathered rows (HealthRec's
+    KD term, cikm_model.py:263); scatter-add backward into the dense table gradient."""
+    return _CosineMean.apply(A.contiguous(), table.contiguous(), _idx(idx.reshape(-1), "idx"))
+
+
 def pair_scores(user_tab: torch.Tensor, item_tab: torch.Tensor, user: torch.Tensor, item: torch.Tensor):
     """`(user_tab[user] * item_tab[item]).sum(1)` (inference_fast / inference_by_user); no autograd."""
     user_tab, item_tab = user_tab.detach(), item_tab.detach()

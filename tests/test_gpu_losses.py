@@ -135,3 +135,21 @@ def test_info_nce_vs_oracle(rows, temperature, norm):
     out.backward()
     close(out, ref.detach().numpy())
     close(hd.grad, h.grad.numpy(), rtol=2e-5)
+
+
+def test_cosine_mean_vs_torch():
+    """HealthRec's KD cosine term: fused gather + cosine + mean vs `F.cosine_similarity(A, T[idx]).mean()`."""
+    from foodrec_b200 import ops
+    torch.manual_seed(8)
+    A = torch.randn(1024, 64).requires_grad_(True)
+    T = torch.randn(5000, 64).requires_grad_(True)
+    idx = torch.randint(0, 5000, (1024,))
+    idx[3] = idx[9]
+    ref = torch.nn.functional.cosine_similarity(A, T[idx], dim=-1).mean()
+    (ref * 1.7).backward()
+    Ad, Td = A.detach().cuda().requires_grad_(True), T.detach().cuda().requires_grad_(True)
+    out = ops.cosine_mean(Ad, Td, idx.cuda())
+    (out * 1.7).backward()
+    close(out, ref.detach().numpy())
+    close(Ad.grad, A.grad.numpy(), rtol=2e-5)
+    close(Td.grad, T.grad.numpy(), rtol=2e-5)

@@ -945,11 +945,14 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
             }
             attr2 = true;
         }
-        static int two_pass = -1;
-        if (two_pass < 0) {
+        // The bounding sweep doubles the MMA work: worth it while the epilogue is the bottleneck (short inner
+        // dimension: full-sort scoring, K = 64), not when a tile already carries many k-blocks (kNN, K = 384..4096).
+        static int two_pass_env = -2;
+        if (two_pass_env == -2) {
             const char *e = getenv("FR_TOPK_TWO_PASS");
-            two_pass = e ? atoi(e) : 1;
+            two_pass_env = e ? atoi(e) : -1;
         }
+        const int two_pass = two_pass_env >= 0 ? two_pass_env : (K <= 256 ? 1 : 0);
         Params2 P2{P, reinterpret_cast<float *>(ws),
                    reinterpret_cast<int *>(reinterpret_cast<float *>(ws) + (size_t)grid * BM * 4 * CAPG), two_pass};
         fr::LaunchTimer _lt2("gemm_topk_kernel_v2", (cudaStream_t)stream);

@@ -147,3 +147,13 @@ def test_rejects_bad_shapes():
         E.gemm_topk(torch.randn(4, 64).cuda(), torch.randn(9, 64).cuda(), 65)
     with pytest.raises(_lib.FoodRecError):
         E.gemm_topk(torch.randn(4, 64).cuda(), torch.randn(900, 64).cuda(), 60)  # no room for bf16 slack
+
+
+def test_wide_inner_dimension_single_sweep():
+    """K = 4096 (image features): many k-blocks per tile, single-sweep path, partial last column block."""
+    from foodrec_b200 import evaluation as E
+    torch.manual_seed(11)
+    feat = torch.randn(700, 4096)
+    val, ind = E.knn_topk(feat.cuda(), 10)
+    xn = feat / feat.norm(dim=-1, keepdim=True)
+    check_topk(val, ind, xn @ xn.t(), 10, atol=5e-6)

@@ -988,6 +988,33 @@ rescore_topk_kernel(const float *__restrict__ A, const int64_t *__restrict__ a_r
         const int c = lane + 32 * t;
         ci[t] = c < kc ? cand[(size_t)row * kc + c] : -1;
         v[t] = -INFINITY;
+    }
+    if (d >= 256) {
+        // wide rows (kNN / centroid features): the whole warp walks one candidate row at a time with coalesced
+        // 128-bit loads and folds by shuffle; lane (c % 32) keeps candidate c's score
+        for (int c = 0; c < kc; ++c) {
+            const int cc = __shfl_sync(0xffffffffu, ci[c >> 5], c & 31);
+            if (cc < 0) continue;
+            const float *b = B + (size_t)cc * d;
+            float s = 0.f;
+            for (int q = lane * 4; q < d; q += 128) {
+                const float4 x = fr::ldg_f4(a + q), y = fr::ldg_f4(b + q);
+                if (metric == 0) {
+                    s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+                } else {
+                    const float e0 = x.x - y.x, e1 = x.y - y.y, e2 = x.z - y.z, e3 = x.w - y.w;
+                    s = fmaf(e0, e0, s); s = fmaf(e1, e1, s); s = fmaf(e2, e2, s); s = fmaf(e3, e3, s);
+                }
+            }
+            s = fr::warp_sum(s);
+            const float sc = metric == 0 ? s * scale + (bias ? __ldg(bias + cc) : 0.f) : -s;
+            if (lane == (c & 31)) v[c >> 5] = sc;
+        }
+    } else {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+
+        v[t] = -INFINITY;
         if (ci[t] >= 0) {
             const float *b = B + (size_t)ci[t] * d;
             float s = 0.f;
@@ -1012,6 +1039,7 @@ rescore_topk_kernel(const float *__restrict__ A, const int64_t *__restrict__ a_r
                 v[t] = -s;
             }
         }
+    }
     }
     for (int o = 0; o < k; ++o) {
         // lane-local best, then warp arg-max (value desc, column asc)

@@ -218,6 +218,30 @@ int fr_infonce_fwd(const float *hidden, int32_t b, int32_t d, float temperature,
 int fr_infonce_bwd(const float *hn, const float *norm, const float *G, const float *lse, int32_t b, int32_t d,
                    float temperature, int32_t normalise, const float *g_out, float *d_hidden, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SCHGN per-pair scorer for full-sort evaluation (d = 64).
+ * Replaces `SCHGN.full_sort_predict` -> `compute_score` (FoodRec/models/schgn.py:318-345, 233-268) with the
+ * two attention levels (:159-184, :186-206) fused; the reference builds python lists over every item,
+ * re-uploads the [I, Dv] image matrix and runs the GCN once PER USER.  The caller precomputes what does not
+ * depend on the user (final rows = table + GCN row; "key" = image of a row under the matching slice of
+ * W_att_ingre / W_att_comp):
+ *   ingre_key / ingre_final / ingre_comp [G + 1, 64]  per ingredient code (code G = padding, all-zero final row)
+ *   img_key [I, 64]        img_emb W_att_ingre[:, image]^T + b_att_ingre
+ *   comps / comp_keys [I, 3, 64]   item, image, health final rows and their W_att_comp[:, component] images
+ *   user_key / user_comp / user_hidden / user_final [nu, 64]   per user of the batch (biases folded in)
+ * fr_schgn_attend writes att [nu, I, 64] (attended ingredient row) and logits [nu, 4, I] (component logits in
+ * the reference order item, ingredients, image, health); fr_schgn_score applies the component softmax over the
+ * reference's `.view(b, -1)` grouping of those logits (schgn.py:198 -- row r reads flat entries 4r .. 4r+3 of
+ * the [4, I] block), then relu(W_concat [u; x; u * x] + b) . output_mlp, and writes scores [nu, I].
+ * fast_tanh != 0 uses 1 - 2 / (1 + exp(2x)) with hardware exp/rcp (|error| ~ 1e-7) instead of tanhf. */
+int fr_schgn_attend(const float *user_key, const float *user_comp, int32_t nu, const int32_t *codes, int32_t slots,
+                    const int32_t *nums, int32_t n_items, const float *ingre_key, const float *ingre_final,
+                    const float *ingre_comp, const float *img_key, const float *comp_keys, const float *h_ingre,
+                    const float *h_comp, int32_t d, int32_t fast_tanh, float *att, float *logits, void *stream);
+int fr_schgn_score(const float *user_final, const float *user_hidden, int32_t nu, const float *W_item,
+                   const float *W_prod, const float *w_out, const float *comps, const float *att, const float *logits,
+                   int32_t n_items, int32_t d, float *scores, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

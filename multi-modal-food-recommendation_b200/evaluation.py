@@ -36,6 +36,17 @@ class HistoryCSR:
         self.ptr = torch.from_numpy(ptr).to(device)
         self.idx = torch.from_numpy(self.idx_host).to(device)
 
+    def mask_scores_(self, scores: torch.Tensor, users: torch.Tensor) -> torch.Tensor:
+        """`scores[r, history(users[r])] = -inf` on a dense `[len(users), n_items]` block (for rankers
+        whose scores are not a GEMM, e.g. SCHGN's pair scorer)."""
+        users = users.to(self.ptr.device).long()
+        lo, hi = self.ptr[users], self.ptr[users + 1]
+        cnt = hi - lo
+        rows = torch.repeat_interleave(torch.arange(users.numel(), device=cnt.device), cnt)
+        off = torch.arange(rows.numel(), device=cnt.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+        scores[rows, self.idx[torch.repeat_interleave(lo, cnt) + off].long()] = float("-inf")
+        return scores
+
 
 _WS = {}
 
@@ -193,6 +204,46 @@ def centroid_topk(features: torch.Tensor, centres: torch.Tensor, k: int = 6, **k
 
 
 # ------------------------------------------------------------------------------ by-user evaluation
+def schgn_pair_scores(*, user_final, user_key, user_comp, user_hidden, W_item, W_prod, w_out, h_ingre, h_comp, codes,
+                      nums, ingre_key, ingre_final, ingre_comp, img_key, comps, comp_keys,
+                      fast_tanh: bool | None = None) -> torch.Tensor:
+    """SCHGN scores `[nu, n_items]` of `nu` users against every item from the user-independent tables
+    (`models.schgn.SCHGN._item_side`): `fr_schgn_attend` + `fr_schgn_score`, FoodRec/models/schgn.py:159-206,
+    233-268, 318-345.  Users are processed in blocks so the `[nu, I, 64]` attended-row scratch stays
+    under ~1 GB."""
+    import os
+    if fast_tanh is None:
+        fast_tanh = os.environ.get("FR_SCHGN_FAST_TANH", "0") == "1"
+    dev = user_final.device
+    if dev.type != "cuda":
+        raise _lib.FoodRecError("schgn_pair_scores needs CUDA tensors (no CPU path)")
+    f32 = [user_final, user_key, user_comp, user_hidden, W_item, W_prod, w_out, h_ingre, h_comp, ingre_key,
+           ingre_final, ingre_comp, img_key, comps, comp_keys]
+    user_final, user_key, user_comp, user_hidden, W_item, W_prod, w_out, h_ingre, h_comp, ingre_key, ingre_final, \
+        ingre_comp, img_key, comps, comp_keys = [t.detach().float().contiguous() for t in f32]
+    nu, d = user_final.shape
+    n_items, slots = codes.shape
+    if codes.dtype != torch.int32 or nums.dtype != torch.int32:
+        raise _lib.FoodRecError("ingredient codes / counts must be int32")
+    scores = torch.empty(nu, n_items, dtype=torch.float32, device=dev)
+    block = max(16, min(256, (1 << 30) // max(1, n_items * d * 4) // 16 * 16))
+    att = torch.empty(min(block, nu), n_items, d, dtype=torch.float32, device=dev)
+    logits = torch.empty(min(block, nu), 4, n_items, dtype=torch.float32, device=dev)
+    st = _lib.stream_ptr()
+    for s in range(0, nu, block):
+        n = min(block, nu - s)
+        _lib.check(_L.fr_schgn_attend(
+            user_key[s:].data_ptr(), user_comp[s:].data_ptr(), n, codes.data_ptr(), slots, nums.data_ptr(), n_items,
+            ingre_key.data_ptr(), ingre_final.data_ptr(), ingre_comp.data_ptr(), img_key.data_ptr(),
+            comp_keys.data_ptr(), h_ingre.data_ptr(), h_comp.data_ptr(), d, int(fast_tanh), att.data_ptr(),
+            logits.data_ptr(), st), "fr_schgn_attend")
+        _lib.check(_L.fr_schgn_score(
+            user_final[s:].data_ptr(), user_hidden[s:].data_ptr(), n, W_item.data_ptr(), W_prod.data_ptr(),
+            w_out.data_ptr(), comps.data_ptr(), att.data_ptr(), logits.data_ptr(), n_items, d,
+            scores[s:].data_ptr(), st), "fr_schgn_score")
+    return scores
+
+
 def evaluate_by_user(model, users, cand_ptr, cand_items, n_pos, neg_num: int = 500):
     """The reference's default evaluation (`eval_by_user: True`): every user is scored against its
     positives followed by `neg_num` sampled negatives (FoodRec/common/trainer.py:231-282,

@@ -177,12 +177,30 @@ def make_dataset(cfg: SynthConfig | str, **overrides) -> SynthFoodData:
     return ds
 
 
-def sample_train_batches(ds: SynthFoodData, batch_size: int, n_batches: int, seed: int = 7):
+def masked_ingredient_task(rng, codes: np.ndarray, counts: np.ndarray, n_ingredients: int, masked_p: float = 0.2):
+    """Vectorised `TrainDataLoader.ssl_task` (FoodRec/utils/dataloader.py:117-143): each real
+    ingredient slot is replaced by the mask token `n_ingredients + 1` with probability `masked_p`
+    and gets a random negative ingredient that is not in the recipe; other slots pass through."""
+    B, L = codes.shape
+    real = np.arange(L)[None, :] < counts[:, None]
+    hide = real & (rng.random((B, L)) < masked_p)
+    neg = rng.integers(0, n_ingredients, size=(B, L))
+    for _ in range(50):
+        clash = hide & (neg[:, :, None] == np.where(real, codes, -1)[:, None, :]).any(-1)
+        if not clash.any():
+            break
+        neg[clash] = rng.integers(0, n_ingredients, size=int(clash.sum()))
+    masked = np.where(hide, n_ingredients + 1, codes)
+    return masked.astype(np.int64), codes.astype(np.int64), np.where(hide, neg, codes).astype(np.int64)
+
+
+def sample_train_batches(ds: SynthFoodData, batch_size: int, n_batches: int, seed: int = 7, schgn: bool = False):
     """Host-side (u, pos, neg) batches with rejection-sampled negatives.
 
     Mirrors what `TrainDataLoader.__getitem__` + default collation hands the model
     (FoodRec/utils/dataloader.py:50-115,145-151): int64 `u_id/pos_i_id/neg_i_id` of shape [B], the
-    two 20-wide ingredient code rows and counts, and the multi-hot health rows.
+    two 20-wide ingredient code rows and counts, and the multi-hot health rows; `schgn=True` adds the
+    image rows (float64, as the loader yields them), calorie levels and the masked-ingredient task.
     """
     rng = np.random.default_rng(seed)
     coo = ds.train_coo_matrix
@@ -205,4 +223,11 @@ def sample_train_batches(ds: SynthFoodData, batch_size: int, n_batches: int, see
             "pos_ingre_num": ds.ingredientNum[p], "neg_ingre_num": ds.ingredientNum[n],
             "pos_hl_mh": ds.health_level_multi_hot[p], "neg_hl_mh": ds.health_level_multi_hot[n],
         })
+        if schgn:  # the extra fields SCHGN.calculate_loss reads (dataloader.py:62-66,75-80)
+            m, ps, ns = masked_ingredient_task(rng, ds.ingredientCodeDict[p], ds.ingredientNum[p], ds.num_ingredients)
+            out[-1].update({
+                "pos_img": ds.embImage[p].astype(np.float64), "neg_img": ds.embImage[n].astype(np.float64),
+                "pos_cl": ds.cal_level[p], "neg_cl": ds.cal_level[n],
+                "masked_ingre_seq": m, "pos_ingre_seq": ps, "neg_ingre_seq": ns,
+            })
     return out

@@ -23,11 +23,17 @@ _m, _mp = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
 _m.pyplot = _mp
 sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = _m, _mp
 
+sys.path.insert(0, ROOT)
+from oracle.schgn import install_pyg_stub  # noqa: E402
+
+install_pyg_stub()  # torch_geometric is not installable offline: GCNConv alone is a restatement (oracle/schgn.py)
+
 from FoodRec.common.loss import BPRLoss, EmbLoss  # noqa: E402
 from FoodRec.common.trainer import metrics_by_user, get_auc_fast  # noqa: E402
 from FoodRec.models.cikm_model import CIKM_Model  # noqa: E402
 from FoodRec.models.lightgcn import LightGCN  # noqa: E402
 from FoodRec.models.pricai_modelx import PRICAI_ModelX  # noqa: E402
+from FoodRec.models.schgn import SCHGN  # noqa: E402
 from FoodRec.utils import utils as ref_utils  # noqa: E402
 from FoodRec.utils.topk_evaluator import TopKEvaluator  # noqa: E402
 
@@ -51,6 +57,8 @@ CFGS = {
     "PRICAI_ModelX": dict(n_ri_layers=2, n_mm_layers=1, n_ui_layers=1, reg_weight=0.01, loss_cl=0.1, knn_k=10,
                           mm_image_weight=0.1),
     "LightGCN": dict(n_layers=2, reg_weight=0.1),
+    "SCHGN": dict(inner_size=256, hidden_dropout_prob=0.5, attention_probs_dropout_prob=0.5, regs=0.01, reg_image=1,
+                  reg_w=0.05, reg_g=0.01, reg_health=0.01, ssl=0.008, SCHGN_ssl=True, neg_sample_num=4),
 }
 
 
@@ -118,6 +126,42 @@ def main():
     g["infer/cand"], g["infer/scores"] = cand, sc.detach().numpy()
     np.savez_compressed(os.path.join(HERE, "clussl_mini.npz"), **g)
     out["clussl"] = len(g)
+
+    # ---------------- SCHGN (reference class executed; GCNConv from oracle/schgn.py; dropout = identity)
+    cfg = Cfg({**BASE, **CFGS["SCHGN"]})
+    torch.manual_seed(999)
+    m = SCHGN(cfg, ds)
+    m.eval()
+    real_dropout = torch.nn.functional.dropout
+    torch.nn.functional.dropout = lambda x, p=0.5, training=True, inplace=False: x
+    g = sd_np(m)
+    g["edges/g2i"], g["edges/i2u"] = m.g2i_edges.numpy(), m.i2u_edges.numpy()
+    x = torch.cat([m.user_embed, m.item_embed, m.ingre_embed_first, m.health_embed], 0)
+    g["gcn/out"] = m.new_gcn(x, torch.cat([m.g2i_edges, m.i2u_edges], 0).t().contiguous()).detach().numpy()
+    sbatches = sample_train_batches(ds, 64, 2, seed=11, schgn=True)
+    for b, batch in enumerate(sbatches):
+        m.zero_grad()
+        losses = m.calculate_loss(to_t(batch))
+        sum(losses).backward()
+        g[f"loss/{b}"] = np.array([float(x) for x in losses], dtype=np.float64)
+        for n_, p_ in m.named_parameters():
+            if p_.grad is not None:
+                g[f"grad/{n_}/{b}"] = p_.grad.detach().numpy().copy()
+        for k in ("masked_ingre_seq", "pos_ingre_seq", "neg_ingre_seq"):
+            g[f"batch/{b}/{k}"] = batch[k]
+    with torch.no_grad():
+        for u in (0, 7, 200):
+            g[f"full_sort/{u}"] = m.full_sort_predict({"u_id": torch.tensor([u])}).numpy()
+        cand = np.concatenate([np.array(ds.validRatings[3]), np.arange(40, 90)])
+        g["by_user/cand"] = cand
+        g["by_user/scores"] = m.inference_by_user({
+            "user_input": torch.full((len(cand),), 3), "item_input": torch.from_numpy(cand),
+            "img_input": torch.from_numpy(ds.embImage[cand]), "ingre_num_input": torch.from_numpy(ds.ingredientNum[cand]),
+            "ingre_input": torch.from_numpy(ds.ingredientCodeDict[cand]),
+            "cal_level_input": torch.from_numpy(ds.cal_level[cand])}).numpy()
+    torch.nn.functional.dropout = real_dropout
+    np.savez_compressed(os.path.join(HERE, "schgn_mini.npz"), **g)
+    out["schgn"] = len(g)
 
     # ---------------- HealthRec
     cfg = Cfg({**BASE, **CFGS["CIKM_Model"]})

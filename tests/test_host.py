@@ -134,3 +134,38 @@ def test_healthrec_and_lightgcn_same_seed_same_state_dict(mini_ds):
         assert sorted(sd.keys()) == ref_keys, set(sd.keys()) ^ set(ref_keys)
         for k in ref_keys:
             assert np.array_equal(sd[k].numpy(), g["sd/" + k]), (cls.__name__, k)
+
+
+SCHGN_CFG = dict(inner_size=256, hidden_dropout_prob=0.5, attention_probs_dropout_prob=0.5, regs=0.01, reg_image=1,
+                 reg_w=0.05, reg_g=0.01, reg_health=0.01, ssl=0.008, SCHGN_ssl=True, neg_sample_num=4)
+
+
+def test_schgn_same_seed_same_state_dict_and_edges(mini_ds):
+    """Parameter names, order, shapes and RNG consumption follow FoodRec/models/schgn.py:46-122."""
+    from foodrec_b200.models.schgn import SCHGN
+    g = load_golden("schgn_mini.npz")
+    torch.manual_seed(999)
+    m = SCHGN(Cfg({**BASE, **SCHGN_CFG}), mini_ds)
+    sd = m.state_dict()
+    ref_keys = [k[3:] for k in g if k.startswith("sd/")]
+    assert list(sd.keys()) == ref_keys
+    for k in ref_keys:
+        assert np.array_equal(sd[k].numpy(), g["sd/" + k]), k
+    assert np.array_equal(m.g2i_edges.numpy(), g["edges/g2i"])
+    assert np.array_equal(m.i2u_edges.numpy(), g["edges/i2u"])
+    assert not m.ingre_embed_second.requires_grad
+
+
+def test_masked_ingredient_task_shapes(mini_ds):
+    from foodrec_b200.synth import sample_train_batches
+    b = sample_train_batches(mini_ds, 64, 1, seed=3, schgn=True)[0]
+    G = mini_ds.num_ingredients
+    real = np.arange(20)[None, :] < b["pos_ingre_num"][:, None]
+    hidden = b["masked_ingre_seq"] == G + 1
+    assert (hidden <= real).all() and hidden.any()
+    assert np.array_equal(b["pos_ingre_seq"], b["pos_ingre_code"])
+    assert np.array_equal(b["neg_ingre_seq"][~hidden], b["pos_ingre_code"][~hidden])
+    # a sampled negative is never one of the recipe's own ingredients (dataloader.py:117-143)
+    for r, c in zip(*np.nonzero(hidden)):
+        assert b["neg_ingre_seq"][r, c] not in set(b["pos_ingre_code"][r, :b["pos_ingre_num"][r]])
+    assert b["pos_img"].dtype == np.float64

@@ -169,3 +169,32 @@ def test_history_mask_oracle():
     _, top = ranking.full_sort_topk(ue, ie, torch.arange(5), 6, ptr, idx)
     for u in range(5):
         assert not set(top[u].tolist()) & set(idx[ptr[u]:ptr[u + 1]].tolist())
+
+
+def test_schgn_oracle_matches_reference_run(mini_ds):
+    """oracle/schgn.py vs tests/golden/schgn_mini.npz (the reference's SCHGN class executed with the
+    GCNConv stand-in; dropout = identity): losses, every parameter gradient, full-sort and by-user scores."""
+    from foodrec_b200.synth import sample_train_batches
+    from oracle import schgn as O
+    g = load_golden("schgn_mini.npz")
+    P = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd/")}
+    ei = O.schgn_edge_index(mini_ds)
+    assert torch.equal(ei, torch.from_numpy(np.concatenate([g["edges/g2i"], g["edges/i2u"]], 0)).t())
+    sizes = (mini_ds.n_users, mini_ds.n_items, mini_ds.num_ingredients, mini_ds.num_calories_level)
+    assert torch.equal(torch.cat(O.gcn_tables(P, ei, sizes), 0), torch.from_numpy(g["gcn/out"]))
+    cfg = dict(regs=0.01, reg_image=1, reg_w=0.05, reg_g=0.01, reg_health=0.01, ssl=0.008, num_hidden_layers=2,
+               num_attention_heads=2)
+    for b, batch in enumerate(sample_train_batches(mini_ds, 64, 2, seed=11, schgn=True)):
+        for k in ("masked_ingre_seq", "neg_ingre_seq"):
+            assert np.array_equal(batch[k], g[f"batch/{b}/{k}"])
+        Pg = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in P.items()}
+        losses = O.calculate_loss(Pg, {k: torch.from_numpy(np.asarray(v)) for k, v in batch.items()}, cfg, ei, sizes)
+        np.testing.assert_allclose([float(x.detach()) for x in losses], g[f"loss/{b}"], rtol=1e-6)
+        sum(losses).backward()
+        for k, ref in g.items():
+            if k.startswith("grad/") and k.endswith(f"/{b}") and "key.bias" not in k:  # d/d(key bias) == 0 exactly
+                got = Pg[k[5:-2]].grad.numpy()
+                assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-12, k
+    for u in (0, 7, 200):
+        s = O.full_sort_scores(P, mini_ds, u, ei, sizes)
+        np.testing.assert_allclose(s.numpy(), g[f"full_sort/{u}"], rtol=0, atol=1e-7)

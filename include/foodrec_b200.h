@@ -233,11 +233,12 @@ int fr_infonce_bwd(const float *hn, const float *norm, const float *G, const flo
  * the reference order item, ingredients, image, health); fr_schgn_score applies the component softmax over the
  * reference's `.view(b, -1)` grouping of those logits (schgn.py:198 -- row r reads flat entries 4r .. 4r+3 of
  * the [4, I] block), then relu(W_concat [u; x; u * x] + b) . output_mlp, and writes scores [nu, I].
- * fast_tanh != 0 uses 1 - 2 / (1 + exp(2x)) with hardware exp/rcp (|error| ~ 1e-7) instead of tanhf. */
+ * tanh(a + b) is evaluated as 1 - 2 / (1 + e^{2a} e^{2b}) with the factors shared across users / items (precise
+ * expf, Newton-refined reciprocal; |error| ~ 2e-7, the order of tanhf's own). */
 int fr_schgn_attend(const float *user_key, const float *user_comp, int32_t nu, const int32_t *codes, int32_t slots,
                     const int32_t *nums, int32_t n_items, const float *ingre_key, const float *ingre_final,
                     const float *ingre_comp, const float *img_key, const float *comp_keys, const float *h_ingre,
-                    const float *h_comp, int32_t d, int32_t fast_tanh, float *att, float *logits, void *stream);
+                    const float *h_comp, int32_t d, float *att, float *logits, void *stream);
 int fr_schgn_score(const float *user_final, const float *user_hidden, int32_t nu, const float *W_item,
                    const float *W_prod, const float *w_out, const float *comps, const float *att, const float *logits,
                    int32_t n_items, int32_t d, float *scores, void *stream);

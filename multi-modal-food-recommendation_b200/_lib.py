@@ -62,7 +62,7 @@ SIGNATURES = {
     "fr_gather_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
     "fr_scatter_add_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
     "fr_pair_scores": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _p, _p]),
-    "fr_schgn_attend": (C.c_int, [_p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
+    "fr_schgn_attend": (C.c_int, [_p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "fr_schgn_score": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p]),
 }
 

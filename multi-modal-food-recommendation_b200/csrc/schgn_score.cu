@@ -18,8 +18,18 @@
 //   schgn_attend_kernel: one warp per item, lanes over the 64 features, 16 users per pass so every
 //     gathered ingredient row is reused 16 times from registers; writes att [nu, I, 64] and logits [nu, 4, I].
 //   schgn_score_kernel: one thread per (user, 2 items); the user's 64x64 matrix
-//     M_u = W_item + W_prod diag(u_final) sits in shared memory (broadcast reads), x in registers.
+//     M_u = W_item + W_prod diag(u_final) sits in shared memory (broadcast reads), x in registers (rows are
+//     loaded coalesced, 16 threads per row, and handed to their owner thread through shared memory).
 // Arithmetic is fp32 throughout (scores feed a top-K that must match the reference's).
+//
+// tanh of a sum of a user-independent and a user-dependent term is evaluated as
+//   tanh(a + b) = 1 - 2 / (1 + e^{2a} e^{2b})
+// with e^{2a} computed once per (item, ingredient, feature) and reused by the 16 users of the pass, e^{2b}
+// once per (user, feature) per CTA, both with the precise expf; what is left per (user, item, ingredient,
+// feature) is one FFMA, one hardware reciprocal refined by a Newton step, and one FFMA into the logit --
+// one MUFU op instead of tanhf's two plus its polynomial branch.  Error ~ 2e-7 absolute, the same order
+// as tanhf's own 2 ulp.  Operands are clamped to +-43 before the exponential (so the product cannot be
+// inf * 0); tanh is saturated in fp32 beyond |x| = 9.1.
 #include "common.cuh"
 
 namespace {
@@ -37,10 +47,15 @@ struct AttendParams {
     int32_t nu, n_items, slots;
 };
 
-template <bool FAST>
-__device__ __forceinline__ float tanh_f(float x) {
-    if (FAST) return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
-    return tanhf(x);
+constexpr float CLAMP = 43.0f;
+// e^{2x}, x clamped so that products of two such factors stay finite or overflow cleanly to +inf
+__device__ __forceinline__ float exp2x(float x) { return expf(2.0f * fminf(fmaxf(x, -CLAMP), CLAMP)); }
+// 1 / (1 + ea * eb) to ~1 ulp: hardware reciprocal + one Newton step (x is in [1, 1e30])
+__device__ __forceinline__ float inv1p(float ea, float eb) {
+    const float x = fminf(fmaf(ea, eb, 1.0f), 1e30f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
 // Sum each of v[0..15] over the 32 lanes with 16 shuffles; lane L ends up holding the total of
@@ -59,16 +74,15 @@ __device__ __forceinline__ float reduce16(float (&v)[UB], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <bool FAST>
 __global__ void __launch_bounds__(ATT_WARPS * 32) schgn_attend_kernel(const AttendParams p) {
-    __shared__ float s_ukey[UB][D];
-    __shared__ float s_ucomp[UB][D];
+    __shared__ float s_ukey[UB][D];   // e^{2 user_key}
+    __shared__ float s_ucomp[UB][D];  // e^{2 user_comp}
     __shared__ float s_logit[ATT_WARPS][UB][MAX_SLOTS];
     const int u0 = blockIdx.y * UB;
     for (int t = threadIdx.x; t < UB * D; t += blockDim.x) {
         const int u = min(u0 + t / D, p.nu - 1);
-        s_ukey[t / D][t % D] = p.user_key[(size_t)u * D + t % D];
-        s_ucomp[t / D][t % D] = p.user_comp[(size_t)u * D + t % D];
+        s_ukey[t / D][t % D] = exp2x(p.user_key[(size_t)u * D + t % D]);
+        s_ucomp[t / D][t % D] = exp2x(p.user_comp[(size_t)u * D + t % D]);
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,18 +94,18 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) schgn_attend_kernel(const Atte
     const float2 pi = *reinterpret_cast<const float2 *>(p.img_key + (size_t)item * D + c2);
     const float2 hi = *reinterpret_cast<const float2 *>(p.h_ingre + c2);
     const float2 hc = *reinterpret_cast<const float2 *>(p.h_comp + c2);
+    const float hi_sum = hi.x + hi.y, hc_sum = hc.x + hc.y;  // sum_d h (1 - 2 r_d) = sum h - 2 sum h r_d
 
     // pass 1: attention logits a[u][j]
     for (int j = 0; j < n; ++j) {
         const int c = __shfl_sync(0xffffffffu, code, j);
-        float2 pe = __ldg(reinterpret_cast<const float2 *>(p.ingre_key + (size_t)c * D + c2));
-        pe.x += pi.x;
-        pe.y += pi.y;
+        const float2 pe = __ldg(reinterpret_cast<const float2 *>(p.ingre_key + (size_t)c * D + c2));
+        const float ex = exp2x(pe.x + pi.x), ey = exp2x(pe.y + pi.y);
         float v[UB];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const float2 uk = *reinterpret_cast<const float2 *>(&s_ukey[u][c2]);
-            v[u] = hi.x * tanh_f<FAST>(pe.x + uk.x) + hi.y * tanh_f<FAST>(pe.y + uk.y);
+            v[u] = fmaf(-2.0f, fmaf(hi.x, inv1p(ex, uk.x), hi.y * inv1p(ey, uk.y)), hi_sum);
         }
         const float tot = reduce16(v, lane);
         if (!(lane & 1)) s_logit[warp][lane >> 1][j] = tot;
@@ -136,9 +150,12 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) schgn_attend_kernel(const Atte
 
     // component logits, reference order: item id, attended ingredients, image, health
     const float *ck = p.comp_keys + (size_t)item * 3 * D + c2;
-    const float2 k_item = *reinterpret_cast<const float2 *>(ck);
-    const float2 k_img = *reinterpret_cast<const float2 *>(ck + D);
-    const float2 k_hl = *reinterpret_cast<const float2 *>(ck + 2 * D);
+    float2 k_item = *reinterpret_cast<const float2 *>(ck);
+    float2 k_img = *reinterpret_cast<const float2 *>(ck + D);
+    float2 k_hl = *reinterpret_cast<const float2 *>(ck + 2 * D);
+    k_item = make_float2(exp2x(k_item.x), exp2x(k_item.y));
+    k_img = make_float2(exp2x(k_img.x), exp2x(k_img.y));
+    k_hl = make_float2(exp2x(k_hl.x), exp2x(k_hl.y));
     const int my_u = u0 + (lane >> 1);
 #pragma unroll
     for (int comp = 0; comp < 4; ++comp) {
@@ -146,8 +163,11 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) schgn_attend_kernel(const Atte
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const float2 uc = *reinterpret_cast<const float2 *>(&s_ucomp[u][c2]);
-            const float2 k = comp == 0 ? k_item : comp == 1 ? q[u] : comp == 2 ? k_img : k_hl;
-            v[u] = hc.x * tanh_f<FAST>(uc.x + k.x) + hc.y * tanh_f<FAST>(uc.y + k.y);
+            const float2 k = comp == 0   ? k_item
+                             : comp == 1 ? make_float2(exp2x(q[u].x), exp2x(q[u].y))
+                             : comp == 2 ? k_img
+                                         : k_hl;
+            v[u] = fmaf(-2.0f, fmaf(hc.x, inv1p(k.x, uc.x), hc.y * inv1p(k.y, uc.y)), hc_sum);
         }
         const float tot = reduce16(v, lane);
         if (!(lane & 1) && my_u < p.nu) p.logits[((size_t)my_u * 4 + comp) * p.n_items + item] = tot;
@@ -161,43 +181,65 @@ struct ScoreParams {
 };
 
 constexpr int SC_THREADS = 128;
-constexpr int IPT = 2;  // items per thread
+constexpr int IPT = 2;                      // items per thread
+constexpr int SC_ITEMS = SC_THREADS * IPT;  // items per CTA
+constexpr int XS = D + 4;                   // row stride of the x tile (floats): conflict-free LDS.128 per quarter-warp
+constexpr int SC_SMEM = (SC_ITEMS * XS + D * D + 2 * D + SC_ITEMS * 4) * (int)sizeof(float);
 
 __global__ void __launch_bounds__(SC_THREADS) schgn_score_kernel(const ScoreParams p) {
-    __shared__ __align__(16) float sM[D][D];
-    __shared__ float sH[D], sW[D];
-    const int u = blockIdx.y;
-    for (int t = threadIdx.x; t < D * D; t += SC_THREADS)
-        sM[t / D][t % D] = fmaf(p.W_prod[t], p.user_final[(size_t)u * D + t % D], p.W_item[t]);
-    if (threadIdx.x < D) {
-        sH[threadIdx.x] = p.user_hidden[(size_t)u * D + threadIdx.x];
-        sW[threadIdx.x] = p.w_out[threadIdx.x];
+    extern __shared__ __align__(16) float smem[];
+    float *sX = smem;                    // [SC_ITEMS][XS]   x = B-weighted component mix, one row per item
+    float *sM = sX + SC_ITEMS * XS;      // [D][D]           M_u = W_item + W_prod diag(u_final)
+    float *sH = sM + D * D;              // [D]              user_hidden[u]
+    float *sW = sH + D;                  // [D]              w_out
+    float *sB = sW + D;                  // [SC_ITEMS][4]    component softmax weights
+    const int u = blockIdx.y, tid = threadIdx.x;
+    const int base = blockIdx.x * SC_ITEMS;
+    for (int t = tid; t < D * D; t += SC_THREADS)
+        sM[t] = fmaf(p.W_prod[t], p.user_final[(size_t)u * D + t % D], p.W_item[t]);
+    if (tid < D) {
+        sH[tid] = p.user_hidden[(size_t)u * D + tid];
+        sW[tid] = p.w_out[tid];
     }
-    __syncthreads();
-    const int base = (blockIdx.x * SC_THREADS + threadIdx.x) * IPT;
-    if (base >= p.n_items) return;
-    const float *lg = p.logits + (size_t)u * 4 * p.n_items;  // [4, I] read as [I, 4]: schgn.py:198
-    float x[IPT][D];
+    // component weights: the [4, I] logits of this user read back as [I, 4] (schgn.py:198)
+    const float *lg = p.logits + (size_t)u * 4 * p.n_items;
 #pragma unroll
     for (int t = 0; t < IPT; ++t) {
-        const int r = min(base + t, p.n_items - 1);
+        const int r = min(base + tid + t * SC_THREADS, p.n_items - 1);
         const float4 l = *reinterpret_cast<const float4 *>(lg + (size_t)4 * r);
         const float m = fmaxf(fmaxf(l.x, l.y), fmaxf(l.z, l.w));
         const float e0 = expf(l.x - m), e1 = expf(l.y - m), e2 = expf(l.z - m), e3 = expf(l.w - m);
         const float inv = 1.0f / (e0 + e1 + e2 + e3);
-        const float b0 = e0 * inv, b1 = e1 * inv, b2 = e2 * inv, b3 = e3 * inv;
-        const float *cr = p.comps + (size_t)r * 3 * D;
-        const float *ar = p.att + ((size_t)u * p.n_items + r) * D;
-#pragma unroll
-        for (int d = 0; d < D; d += 4) {
-            const float4 ci = fr::ldg_f4(cr + d), cm = fr::ldg_f4(cr + D + d), ch = fr::ldg_f4(cr + 2 * D + d);
-            const float4 ca = fr::ldg_f4(ar + d);
-            x[t][d + 0] = b0 * ci.x + b1 * ca.x + b2 * cm.x + b3 * ch.x;
-            x[t][d + 1] = b0 * ci.y + b1 * ca.y + b2 * cm.y + b3 * ch.y;
-            x[t][d + 2] = b0 * ci.z + b1 * ca.z + b2 * cm.z + b3 * ch.z;
-            x[t][d + 3] = b0 * ci.w + b1 * ca.w + b2 * cm.w + b3 * ch.w;
+        *reinterpret_cast<float4 *>(sB + 4 * (tid + t * SC_THREADS)) = make_float4(e0 * inv, e1 * inv, e2 * inv, e3 * inv);
+    }
+    __syncthreads();
+    // x rows, loaded coalesced: 16 threads per row (one float4 each), 8 rows per pass
+    {
+        const int sub = (tid & 15) * 4, rr = tid >> 4;
+#pragma unroll 4
+        for (int row = rr; row < SC_ITEMS; row += SC_THREADS / 16) {
+            const int r = min(base + row, p.n_items - 1);
+            const float4 b = *reinterpret_cast<const float4 *>(sB + 4 * row);
+            const float *cr = p.comps + (size_t)r * 3 * D + sub;
+            const float4 ci = fr::ldg_f4(cr), cm = fr::ldg_f4(cr + D), ch = fr::ldg_f4(cr + 2 * D);
+            const float4 ca = fr::ldg_f4(p.att + ((size_t)u * p.n_items + r) * D + sub);
+            float4 x;
+            x.x = b.x * ci.x + b.y * ca.x + b.z * cm.x + b.w * ch.x;
+            x.y = b.x * ci.y + b.y * ca.y + b.z * cm.y + b.w * ch.y;
+            x.z = b.x * ci.z + b.y * ca.z + b.z * cm.z + b.w * ch.z;
+            x.w = b.x * ci.w + b.y * ca.w + b.z * cm.w + b.w * ch.w;
+            *reinterpret_cast<float4 *>(sX + row * XS + sub) = x;
         }
     }
+    __syncthreads();
+    float x[IPT][D];
+#pragma unroll
+    for (int t = 0; t < IPT; ++t)
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(sX + (tid + t * SC_THREADS) * XS + d);
+            x[t][d] = v.x, x[t][d + 1] = v.y, x[t][d + 2] = v.z, x[t][d + 3] = v.w;
+        }
     float score[IPT];
 #pragma unroll
     for (int t = 0; t < IPT; ++t) score[t] = 0.0f;
@@ -208,7 +250,7 @@ __global__ void __launch_bounds__(SC_THREADS) schgn_score_kernel(const ScorePara
         for (int t = 0; t < IPT; ++t) h[t][0] = sH[e], h[t][1] = h[t][2] = h[t][3] = 0.0f;
 #pragma unroll
         for (int d = 0; d < D; d += 4) {
-            const float4 m = *reinterpret_cast<const float4 *>(&sM[e][d]);
+            const float4 m = *reinterpret_cast<const float4 *>(sM + e * D + d);
 #pragma unroll
             for (int t = 0; t < IPT; ++t) {
                 h[t][0] = fmaf(m.x, x[t][d + 0], h[t][0]);
@@ -223,8 +265,10 @@ __global__ void __launch_bounds__(SC_THREADS) schgn_score_kernel(const ScorePara
             score[t] = fmaf(w, fmaxf((h[t][0] + h[t][1]) + (h[t][2] + h[t][3]), 0.0f), score[t]);
     }
 #pragma unroll
-    for (int t = 0; t < IPT; ++t)
-        if (base + t < p.n_items) p.scores[(size_t)u * p.n_items + base + t] = score[t];
+    for (int t = 0; t < IPT; ++t) {
+        const int r = base + tid + t * SC_THREADS;
+        if (r < p.n_items) p.scores[(size_t)u * p.n_items + r] = score[t];
+    }
 }
 
 }  // namespace
@@ -233,7 +277,7 @@ extern "C" int fr_schgn_attend(const float *user_key, const float *user_comp, in
                                int32_t slots, const int32_t *nums, int32_t n_items, const float *ingre_key,
                                const float *ingre_final, const float *ingre_comp, const float *img_key,
                                const float *comp_keys, const float *h_ingre, const float *h_comp, int32_t d,
-                               int32_t fast_tanh, float *att, float *logits, void *stream) {
+                               float *att, float *logits, void *stream) {
     FR_REQUIRE(d == D, "fr_schgn_attend: embedding width %d unsupported (the model fixes 64)", d);
     FR_REQUIRE(nu >= 0 && n_items >= 0 && slots >= 1 && slots <= MAX_SLOTS,
                "fr_schgn_attend: bad extents (nu=%d, n_items=%d, slots=%d; at most %d slots)", nu, n_items, slots,
@@ -248,10 +292,7 @@ extern "C" int fr_schgn_attend(const float *user_key, const float *user_comp, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     fr::LaunchTimer timer("schgn_attend", st);
     dim3 grid((n_items + ATT_WARPS - 1) / ATT_WARPS, (nu + UB - 1) / UB);
-    if (fast_tanh)
-        schgn_attend_kernel<true><<<grid, ATT_WARPS * 32, 0, st>>>(p);
-    else
-        schgn_attend_kernel<false><<<grid, ATT_WARPS * 32, 0, st>>>(p);
+    schgn_attend_kernel<<<grid, ATT_WARPS * 32, 0, st>>>(p);
     return fr::check_launch("fr_schgn_attend");
 }
 
@@ -266,7 +307,13 @@ extern "C" int fr_schgn_score(const float *user_final, const float *user_hidden,
     ScoreParams p{user_final, user_hidden, W_item, W_prod, w_out, comps, att, logits, scores, nu, n_items};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     fr::LaunchTimer timer("schgn_score", st);
-    dim3 grid((n_items + SC_THREADS * IPT - 1) / (SC_THREADS * IPT), nu);
-    schgn_score_kernel<<<grid, SC_THREADS, 0, st>>>(p);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(schgn_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM) != cudaSuccess)
+            return fr::check_launch("fr_schgn_score (shared-memory opt-in)");
+        configured = true;
+    }
+    dim3 grid((n_items + SC_ITEMS - 1) / SC_ITEMS, nu);
+    schgn_score_kernel<<<grid, SC_THREADS, SC_SMEM, st>>>(p);
     return fr::check_launch("fr_schgn_score");
 }

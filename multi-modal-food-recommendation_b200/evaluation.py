@@ -205,15 +205,11 @@ def centroid_topk(features: torch.Tensor, centres: torch.Tensor, k: int = 6, **k
 
 # ------------------------------------------------------------------------------ by-user evaluation
 def schgn_pair_scores(*, user_final, user_key, user_comp, user_hidden, W_item, W_prod, w_out, h_ingre, h_comp, codes,
-                      nums, ingre_key, ingre_final, ingre_comp, img_key, comps, comp_keys,
-                      fast_tanh: bool | None = None) -> torch.Tensor:
+                      nums, ingre_key, ingre_final, ingre_comp, img_key, comps, comp_keys) -> torch.Tensor:
     """SCHGN scores `[nu, n_items]` of `nu` users against every item from the user-independent tables
     (`models.schgn.SCHGN._item_side`): `fr_schgn_attend` + `fr_schgn_score`, FoodRec/models/schgn.py:159-206,
     233-268, 318-345.  Users are processed in blocks so the `[nu, I, 64]` attended-row scratch stays
     under ~1 GB."""
-    import os
-    if fast_tanh is None:
-        fast_tanh = os.environ.get("FR_SCHGN_FAST_TANH", "0") == "1"
     dev = user_final.device
     if dev.type != "cuda":
         raise _lib.FoodRecError("schgn_pair_scores needs CUDA tensors (no CPU path)")
@@ -235,7 +231,7 @@ def schgn_pair_scores(*, user_final, user_key, user_comp, user_hidden, W_item, W
         _lib.check(_L.fr_schgn_attend(
             user_key[s:].data_ptr(), user_comp[s:].data_ptr(), n, codes.data_ptr(), slots, nums.data_ptr(), n_items,
             ingre_key.data_ptr(), ingre_final.data_ptr(), ingre_comp.data_ptr(), img_key.data_ptr(),
-            comp_keys.data_ptr(), h_ingre.data_ptr(), h_comp.data_ptr(), d, int(fast_tanh), att.data_ptr(),
+            comp_keys.data_ptr(), h_ingre.data_ptr(), h_comp.data_ptr(), d, att.data_ptr(),
             logits.data_ptr(), st), "fr_schgn_attend")
         _lib.check(_L.fr_schgn_score(
             user_final[s:].data_ptr(), user_hidden[s:].data_ptr(), n, W_item.data_ptr(), W_prod.data_ptr(),

@@ -61,6 +61,23 @@ def main():
     for _ in range(5):
         step()
     out["train_step_ms"] = round(timed(step, 30), 3)
+    if os.environ.get("FR_TORCH_PROFILE"):
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60), file=sys.stderr)
+    try:  # the same step as one CUDA-graph replay (static batch buffers, capturable Adam)
+        from foodrec_b200.train import GraphedTrainStep
+        opt_g = torch.optim.Adam(m.parameters(), lr=5e-4, fused=True, capturable=True)
+        gstep = GraphedTrainStep(m, opt_g, batches[0], keys=tuple(batches[0].keys()))
+        for b in batches:
+            gstep(b)
+        out["train_step_graph_ms"] = round(timed(lambda: gstep(batches[state["i"] % len(batches)]), 30), 3)
+        out["graph_losses"] = [round(float(x), 4) for x in gstep(batches[1])]
+    except Exception as exc:  # noqa: BLE001
+        out["train_step_graph_error"] = repr(exc)[:300]
     x = torch.cat([m.user_embed, m.item_embed, m.ingre_embed_first, m.health_embed], 0).detach()
     ei = m._edges(m.g2i_edges, m.i2u_edges)
     g = m.new_gcn.plan(ei, x.shape[0])
@@ -77,21 +94,14 @@ def main():
         m.full_sort_scores(users[:16])
         torch.cuda.synchronize()
         out["item_side_first_call_s"] = round(time.time() - t1, 2)
-        for mode in ("0", "1"):
-            os.environ["FR_SCHGN_FAST_TANH"] = mode
+        m.full_sort_scores(users)
+        ms = timed(lambda: m.full_sort_scores(users), 3)
+        with _lib.kernel_profile() as prof:
             m.full_sort_scores(users)
-            ms = timed(lambda: m.full_sort_scores(users), 3)
-            with _lib.kernel_profile() as prof:
-                m.full_sort_scores(users)
-            key = "fast" if mode == "1" else "precise"
-            out[f"full_sort_{key}_ms"] = round(ms, 2)
-            out[f"full_sort_{key}_users_per_s"] = round(nu / ms * 1e3, 1)
-            out[f"kernels_{key}_ms"] = {k: round(us / 1e3, 3) for k, (n, us) in prof.result.items()}
-        os.environ["FR_SCHGN_FAST_TANH"] = "0"
+        out["full_sort_ms"] = round(ms, 2)
+        out["full_sort_users_per_s"] = round(nu / ms * 1e3, 1)
+        out["kernels_ms"] = {k: round(us / 1e3, 3) for k, (n, us) in prof.result.items()}
         a = m.full_sort_scores(users[:64])
-        os.environ["FR_SCHGN_FAST_TANH"] = "1"
-        b = m.full_sort_scores(users[:64])
-        out["fast_vs_precise_max_abs"] = float((a - b).abs().max())
         out["score_std"] = float(a.std())
         t1 = time.time()
         v, i = m.full_sort_topk(users, 20)

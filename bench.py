@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--scale", default="C2")
     ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-schgn", action="store_true", help="skip the SCHGN side measurement")
     ap.add_argument("--eager", action="store_true", help="drop-in eager step (no CUDA graph)")
     ap.add_argument("--foreach-adam", action="store_true", help="torch's default foreach Adam instead of fused=True")
     args = ap.parse_args()
@@ -370,6 +371,9 @@ def main():
     }
     if world == 1:
         line["eval_c4_slice"] = _bench_eval_c4(dev, tpeak)
+    if world == 1 and not args.no_schgn:
+        torch.set_num_threads(os.cpu_count() or 1)
+        line["schgn"] = _bench_schgn(ds, dev, steps_per_epoch, not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         oracle = OracleClussl(ds, sd0, cfg["learning_rate"])

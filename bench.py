@@ -386,6 +386,88 @@ def main():
     return 0
 
 
+SCHGN_CFG = dict(embedding_size=64, train_batch_size=BATCH, is_multimodal_model=True, end2end=False,
+                 num_attention_heads=2, num_hidden_layers=2, hidden_act="gelu", inner_size=256, hidden_dropout_prob=0.5,
+                 attention_probs_dropout_prob=0.5, regs=0.01, reg_image=1, reg_w=0.05, reg_g=0.01, reg_health=0.01,
+                 ssl=0.008, SCHGN_ssl=True, neg_sample_num=4, learning_rate=0.0005)  # configs/model/SCHGN.yaml
+
+
+def _bench_schgn(ds, dev, steps_per_epoch, cpu_baseline):
+    """BASELINE.json configs[1] names SCHGN on this graph: its train step (GCN on the propagation kernel,
+    kernel gathers, batch-sized scorer in torch; one CUDA-graph replay per batch) and its full sort (fused pair
+    scorer, 256 users) -- reported beside the headline, each with the CPU restatement timed on the host."""
+    from foodrec_b200 import _lib
+    from foodrec_b200.models.schgn import SCHGN
+    from foodrec_b200.synth import sample_train_batches
+    from foodrec_b200.train import GraphedTrainStep
+    cfg = Cfg({**SCHGN_CFG, "device": str(dev)})
+    torch.manual_seed(999)
+    model = SCHGN(cfg, ds)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(dev).train()
+    host = sample_train_batches(ds, BATCH, 4, seed=21, schgn=True)
+    batches = [{k: torch.from_numpy(np.asarray(v)).to(dev) for k, v in b.items()} for b in host]
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["learning_rate"], fused=True, capturable=True)
+    l0 = _lib.launch_count()
+    step = GraphedTrainStep(model, opt, batches[0], keys=tuple(batches[0].keys()), warmup=3)
+    launches_per_step = (_lib.launch_count() - l0) / 4          # 3 eager warm-up steps + the capture pass
+    for i in range(5):
+        step(batches[i % 4])
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    n_steps = 50
+    for i in range(n_steps):
+        step(batches[i % 4])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n_steps
+    n_nodes = ds.n_users + ds.n_items + ds.num_ingredients + ds.num_calories_level
+    out = {"workload": f"SCHGN on the same graph: GCN over {n_nodes} nodes, B={BATCH}, {ds.image_size}-d image rows, "
+                       f"masked-ingredient task, Adam; dropout on",
+           "train_ms_per_step": ms, "train_epochs_per_s": 1.0 / (steps_per_epoch * ms * 1e-3),
+           "library_launches_per_step": launches_per_step}
+    model.eval()
+    users = torch.arange(256, device=dev)
+    with torch.no_grad():
+        model.full_sort_topk(users, 20)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(2):
+            model.full_sort_topk(users, 20)
+        b.record()
+        torch.cuda.synchronize()
+    fs_ms = a.elapsed_time(b) / 2
+    out["full_sort"] = {"workload": f"256 users x {ds.n_items} items through the fused pair scorer + top-20",
+                        "ms": fs_ms, "users_per_s": 256 / (fs_ms * 1e-3), "pairs_per_s": 256 * ds.n_items / (fs_ms * 1e-3)}
+    if cpu_baseline:
+        from oracle import schgn as O
+        P = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and k != "ingre_embed_second")
+             for k, v in sd0.items()}
+        popt = torch.optim.Adam([v for v in P.values() if v.requires_grad], lr=cfg["learning_rate"])
+        ei = O.schgn_edge_index(ds)
+        sizes = (ds.n_users, ds.n_items, ds.num_ingredients, ds.num_calories_level)
+
+        def cpu_step(hb):
+            popt.zero_grad()
+            sum(O.calculate_loss(P, {k: torch.from_numpy(np.asarray(v)) for k, v in hb.items()}, cfg, ei, sizes)).backward()
+            popt.step()
+        cpu_step(host[0])
+        t0 = time.perf_counter()
+        for hb in host[1:3]:
+            cpu_step(hb)
+        cpu_ms = (time.perf_counter() - t0) / 2 * 1e3
+        with torch.no_grad():
+            Pd = {k: v.detach() for k, v in P.items()}
+            t0 = time.perf_counter()
+            O.full_sort_scores(Pd, ds, 3, ei, sizes)
+            cpu_fs = time.perf_counter() - t0
+        out["cpu_baseline"] = {"kind": "port", "cores": torch.get_num_threads(), "train_ms_per_step": cpu_ms,
+                               "full_sort_users_per_s": 1.0 / cpu_fs,
+                               "sample": "2 train batches (dropout = identity); 1 user against all items"}
+    return out
+
+
 def _bench_eval(model, ds, dev, rank, world, barrier):
     """Full-sort evaluation of every user (sharded by user over the ranks), k = 20, history mask."""
     from foodrec_b200 import evaluation as E

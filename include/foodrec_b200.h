@@ -243,6 +243,27 @@ int fr_schgn_score(const float *user_final, const float *user_hidden, int32_t nu
                    const float *W_prod, const float *w_out, const float *comps, const float *att, const float *logits,
                    int32_t n_items, int32_t d, float *scores, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row-partitioned multi-GPU propagation over peer memory (one process per GPU, one NVLink/NVSwitch node).
+ * The reference is single-GPU; the baseline exchange is one NCCL all-gather per layer
+ * (dist.py).  Here the all-gather of layer l+1's input is fused into layer l's kernel: the push epilogue
+ * stores every finished output row at row `row_off + r` of `n_peers` (<= 8) full-size tables, one per rank,
+ * mapped with CUDA IPC.  Y may be NULL (only the pushed copies are wanted).  Ranks order themselves with the
+ * caller's stream-ordered barrier; no kernel waits on another rank.
+ *   fr_peer_alloc   cudaMalloc (zeroed) + 64-byte IPC handle to send to the other ranks
+ *   fr_peer_open    map another rank's table from its handle;  fr_peer_close / fr_peer_free  undo the two
+ *   fr_push_rows    the same exchange for rows no SpMM produced (the layer-0 input) */
+int fr_peer_alloc(int64_t bytes, void **ptr, void *handle64);
+int fr_peer_open(const void *handle64, void **ptr);
+int fr_peer_close(void *ptr);
+int fr_peer_free(void *ptr);
+int fr_push_rows(const float *src, int64_t rows, int32_t d, float *const *peers_host, int32_t n_peers, int64_t row_off,
+                 void *stream);
+int fr_spmm_csr_f32_push(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                         const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z, float alpha,
+                         float beta, float *Y, float *partial, int32_t *counters, float *const *peers_host,
+                         int32_t n_peers, int64_t row_off, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,13 @@ struct Split {
     // y_mask[r] receives whether output row r has any nonzero, for the next layer.
     const unsigned char *x_mask;
     unsigned char *y_mask;
+    // Optional push epilogue (row-partitioned multi-GPU propagation): every finished output row is also
+    // stored at row `row_off + r` of up to 8 full-size tables, one per rank of the node (peer memory over
+    // NVLink, this rank's own copy included) -- the all-gather of the next layer's input, fused into the
+    // producing kernel so the transfer overlaps the gathers tile by tile.
+    float *peer[8];
+    int n_peers;
+    long long row_off;
 };
 
 template <int D>
@@ -56,10 +63,10 @@ __device__ __forceinline__ float4 reduce_subgroups(float4 a) {
     return a;
 }
 
-template <int D, int ACT>
+template <int D, int ACT, bool PUSH = false>
 __device__ __forceinline__ bool epilogue_store(float4 acc, int row, int off, const float *__restrict__ Z,
                                                float alpha, float beta, const float *__restrict__ bias,
-                                               float *__restrict__ Y) {
+                                               float *__restrict__ Y, const Split *sp = nullptr) {
     float4 y = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
     const size_t o = (size_t)row * D + off;
     if (Z != nullptr) {
@@ -79,7 +86,13 @@ __device__ __forceinline__ bool epilogue_store(float4 acc, int row, int off, con
         y.z = tanhf(y.z);
         y.w = tanhf(y.w);
     }
-    *reinterpret_cast<float4 *>(Y + o) = y;
+    if (!PUSH || Y != nullptr) *reinterpret_cast<float4 *>(Y + o) = y;
+    if (PUSH) {
+        const size_t po = (size_t)(sp->row_off + row) * D + off;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)     // static indices: the table pointers stay in the kernel-parameter bank
+            if (q < sp->n_peers) *reinterpret_cast<float4 *>(sp->peer[q] + po) = y;
+    }
     return (y.x != 0.f) | (y.y != 0.f) | (y.z != 0.f) | (y.w != 0.f);
 }
 
@@ -320,7 +333,7 @@ spmm_bulk_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__re
 // per-row bookkeeping of the warp-per-segment kernel (D = 64: 8 lanes x 2 float4, four rows per warp),
 // and the shuffle / address / predicate work of a step is shared by 4 nonzeros.  Groups of one warp take
 // adjacent segments of the length-sorted plan, so their trip counts match.
-template <int D, int LPR, int U, int ACT, bool SPLIT, bool MASKED>
+template <int D, int LPR, int U, int ACT, bool SPLIT, bool MASKED, bool PUSH = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, FR_GROUP_MIN_BLOCKS)
 spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
                   const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
@@ -386,8 +399,8 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
         bool nz = false;
 #pragma unroll
         for (int t = 0; t < VPL; ++t)
-            nz |= epilogue_store<D, ACT>(acc[t], s.x, 4 * (lg + LPR * t), (Z != nullptr && s.x >= sp.z_split) ? sp.Z1_adj : Z,
-                                         alpha, beta, bias, Y);
+            nz |= epilogue_store<D, ACT, PUSH>(acc[t], s.x, 4 * (lg + LPR * t),
+                                               (Z != nullptr && s.x >= sp.z_split) ? sp.Z1_adj : Z, alpha, beta, bias, Y, &sp);
         if (sp.y_mask != nullptr) {
             nz = __any_sync(gmask, nz);
             if (lg == 0) sp.y_mask[s.x] = nz ? 1 : 0;
@@ -421,8 +434,8 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
             for (int u = 0; u < 8; ++u) fr::add4(tot, p8[u]);
         }
         for (; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(pp + (size_t)k * D));
-        nz_long |= epilogue_store<D, ACT>(tot, lr.w, 4 * (lg + LPR * t), (Z != nullptr && lr.w >= sp.z_split) ? sp.Z1_adj : Z,
-                                          alpha, beta, bias, Y);
+        nz_long |= epilogue_store<D, ACT, PUSH>(tot, lr.w, 4 * (lg + LPR * t),
+                                                (Z != nullptr && lr.w >= sp.z_split) ? sp.Z1_adj : Z, alpha, beta, bias, Y, &sp);
     }
     if (sp.y_mask != nullptr) {
         nz_long = __any_sync(gmask, nz_long);
@@ -443,6 +456,16 @@ int launch_group_shape(const int4 *seg, int64_t n_seg, const int4 *lrows, const 
         return FR_EUNSUPPORTED;
     }
     fr::LaunchTimer _lt("spmm_group_kernel", st);
+    if (sp.n_peers > 0) {           // push epilogue: default shape, no activation, single-table operands
+        if constexpr (ACT == 0 && LPR == 8 && U == 4) {
+            spmm_group_kernel<D, LPR, U, 0, false, false, true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+                seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
+            return fr::check_launch("fr_spmm_csr_f32_push");
+        } else {
+            fr::set_error("fr_spmm_csr_f32_push: needs act = 0 and the default kernel shape");
+            return FR_EUNSUPPORTED;
+        }
+    }
     if (sp.x_split != 0x7fffffff)   // two-segment gather only where it is used (first layer of a forward)
         spmm_group_kernel<D, LPR, U, ACT, true, false><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
             seg, n_seg, lrows, col, val, X, Z, alpha, beta, bias, Y, partial, counters, sp);
@@ -625,10 +648,11 @@ static int spmm_entry(const int32_t *seg, int64_t n_seg, const int32_t *long_row
                       const int32_t *col_idx, const float *val, int32_t d, const float *X0, const float *X1,
                       int32_t x_split, const float *Z0, const float *Z1, int32_t z_split, float alpha,
                       float beta, const float *bias, int32_t act, float *Y, float *partial,
-                      int32_t *counters, const uint8_t *x_mask, uint8_t *y_mask, void *stream) {
+                      int32_t *counters, const uint8_t *x_mask, uint8_t *y_mask, void *stream,
+                      float *const *peers_host = nullptr, int32_t n_peers = 0, int64_t row_off = 0) {
     FR_REQUIRE(n_seg >= 0 && n_long >= 0, "fr_spmm_csr_f32: negative extent");
     if (n_seg == 0) return FR_OK;
-    FR_REQUIRE(seg && X0 && Y, "fr_spmm_csr_f32: null seg/X/Y");
+    FR_REQUIRE(seg && X0 && (Y || n_peers > 0), "fr_spmm_csr_f32: null seg/X/Y");
     FR_REQUIRE(n_long == 0 || (long_rows && partial && counters), "fr_spmm_csr_f32: long rows need workspace");
     FR_REQUIRE(act == 0 || act == 1, "fr_spmm_csr_f32: act must be 0 or 1");
     FR_REQUIRE((((uintptr_t)X0 | (uintptr_t)X1 | (uintptr_t)Y | (uintptr_t)Z0 | (uintptr_t)Z1 | (uintptr_t)bias |
@@ -645,6 +669,18 @@ static int spmm_entry(const int32_t *seg, int64_t n_seg, const int32_t *long_row
     FR_REQUIRE(x_mask == nullptr || X1 == nullptr, "fr_spmm_csr_f32_masked: a row mask needs a single-table X");
     sp.x_mask = x_mask;
     sp.y_mask = y_mask;
+    FR_REQUIRE(n_peers >= 0 && n_peers <= 8 && row_off >= 0 && (n_peers == 0 || peers_host != nullptr),
+               "fr_spmm_csr_f32_push: 1..8 peer tables");
+    FR_REQUIRE(n_peers == 0 || (X1 == nullptr && Z1 == nullptr && x_mask == nullptr && y_mask == nullptr && act == 0 &&
+                                spmm_impl() == 2),
+               "fr_spmm_csr_f32_push: single-table operands, no masks, no activation, default kernel");
+    sp.n_peers = n_peers;
+    sp.row_off = row_off;
+    for (int q = 0; q < 8; ++q) {
+        sp.peer[q] = q < n_peers ? peers_host[q] : nullptr;
+        FR_REQUIRE(q >= n_peers || (sp.peer[q] != nullptr && ((uintptr_t)sp.peer[q] & 15) == 0 && sp.peer[q] != X0),
+                   "fr_spmm_csr_f32_push: peer tables must be non-null, 16-byte aligned and distinct from X");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int4 *sg = reinterpret_cast<const int4 *>(seg);
     const int4 *lr = reinterpret_cast<const int4 *>(long_rows);
@@ -665,6 +701,15 @@ extern "C" int fr_spmm_csr_f32_split(const int32_t *seg, int64_t n_seg, const in
                                      int32_t *counters, void *stream) {
     return spmm_entry(seg, n_seg, long_rows, n_long, col_idx, val, d, X0, X1, x_split, Z0, Z1, z_split, alpha, beta, bias, act,
                       Y, partial, counters, nullptr, nullptr, stream);
+}
+
+extern "C" int fr_spmm_csr_f32_push(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,
+                                    const int32_t *col_idx, const float *val, int32_t d, const float *X, const float *Z,
+                                    float alpha, float beta, float *Y, float *partial, int32_t *counters,
+                                    float *const *peers_host, int32_t n_peers, int64_t row_off, void *stream) {
+    FR_REQUIRE(n_peers >= 1, "fr_spmm_csr_f32_push: at least one destination table");
+    return spmm_entry(seg, n_seg, long_rows, n_long, col_idx, val, d, X, nullptr, 0, Z, nullptr, 0, alpha, beta, nullptr, 0, Y,
+                      partial, counters, nullptr, nullptr, stream, peers_host, n_peers, row_off);
 }
 
 extern "C" int fr_spmm_csr_f32_masked(const int32_t *seg, int64_t n_seg, const int32_t *long_rows, int64_t n_long,

@@ -11,6 +11,12 @@ symmetric graphs the backward is the same thing on the gathered upstream gradien
 (`dX_p = S_p . all_gather(dY)`), i.e. one all-gather per layer in each direction and no reduce-scatter.
 The layer-mean epilogue (Horner form, see ops.py) is row-local.
 
+`propagate_mean_pushed` is the same computation with the exchange fused into the kernel: the SpMM's
+epilogue stores each finished row into a full-size table on EVERY rank (CUDA-IPC peer memory over
+NVLink / NVSwitch), so the next layer's input is complete when the kernels end and the transfer
+overlaps the gathers; a 4-byte all-reduce orders the ranks.  Results are bit-identical to the
+all-gather path (same local kernel, same inputs).
+
 Evaluation.  Users are sharded across ranks, the item table is replicated; each rank runs the fused
 score + top-K kernel on its users and the `[U/P, k]` results are gathered once at the end.
 """
@@ -99,6 +105,126 @@ def _device_spmm(graph, x_full, z, alpha, beta):
 def propagate_mean_partitioned(pg: RowPartitionedGraph, ego_local: torch.Tensor, n_layers: int, group=None, spmm=None):
     """Differentiable row-partitioned layer-mean propagation (this rank's rows in, this rank's rows out)."""
     return _PartitionedPropagate.apply(ego_local, pg, n_layers, spmm or _device_spmm, group)
+
+
+# ------------------------------------------------------- propagation with the exchange fused into the kernel
+class _DevicePtr:
+    """Raw device allocation exposed through `__cuda_array_interface__` so torch can view it."""
+
+    def __init__(self, ptr, rows, d):
+        self.__cuda_array_interface__ = {"shape": (rows, d), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerTables:
+    """Two full-size `[n_padded, d]` fp32 tables on every rank of the node, each mapped into every other
+    rank with CUDA IPC (`fr_peer_alloc` / `fr_peer_open`).  `peers[b]` is the ctypes array of table b's
+    address on ranks 0..world-1 (this rank's own copy included), the destination list of the push
+    epilogue; `table(b)` views this rank's copy."""
+
+    def __init__(self, n_padded: int, d: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self.group = _lib, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise _lib.FoodRecError("peer tables span one node: at most 8 ranks")
+        self.n_padded, self.d, self.device = n_padded, d, torch.device(device)
+        self.own, handles = [], []
+        for _ in range(2):
+            ptr, h = C.c_void_p(), C.create_string_buffer(64)
+            _lib.check(_lib.lib.fr_peer_alloc(n_padded * d * 4, C.byref(ptr), h), "fr_peer_alloc")
+            self.own.append(ptr.value)
+            handles.append(h.raw)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=group)
+        self.opened, self.peers = [], []
+        for b in range(2):
+            addrs = []
+            for q in range(self.world):
+                if q == self.rank:
+                    addrs.append(self.own[b])
+                    continue
+                ptr = C.c_void_p()
+                _lib.check(_lib.lib.fr_peer_open(everyone[q][b], C.byref(ptr)), "fr_peer_open")
+                self.opened.append(ptr.value)
+                addrs.append(ptr.value)
+            self.peers.append((C.c_void_p * self.world)(*addrs))
+        self._views = [torch.as_tensor(_DevicePtr(p, n_padded, d), device=self.device) for p in self.own]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.barrier()
+
+    def table(self, b: int) -> torch.Tensor:
+        return self._views[b]
+
+    def barrier(self):
+        """Stream-ordered barrier between ranks: a 4-byte all-reduce (the collective library does the
+        waiting; no kernel of this package spins on another rank)."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        self.barrier()
+        torch.cuda.synchronize(self.device)
+        self._views = []
+        for p in self.opened:
+            self._lib.check(self._lib.lib.fr_peer_close(p), "fr_peer_close")
+        self.opened = []
+        dist.barrier(group=self.group)
+        for p in self.own:
+            self._lib.check(self._lib.lib.fr_peer_free(p), "fr_peer_free")
+        self.own = []
+
+
+def propagate_mean_pushed_raw(pg: RowPartitionedGraph, ego_local: torch.Tensor, n_layers: int, tables: PeerTables):
+    """`mean_l S^l ego` for this rank's rows with the per-layer exchange fused into the producing kernel:
+    layer l's epilogue stores its output rows into table (l+1) % 2 of every rank (`fr_spmm_csr_f32_push`),
+    so there is no all-gather; the layer-0 input is exchanged by `fr_push_rows`.  A 4-byte all-reduce orders
+    the ranks after every exchange and at the end of the call (table reuse by the next call)."""
+    from . import _lib, ops
+    L = _lib.lib
+    if n_layers == 0:
+        return ego_local.clone()
+    g, d = pg.local, ego_local.shape[1]
+    if (tables.n_padded, tables.d) != (pg.n_padded, d):
+        raise _lib.FoodRecError("peer tables do not match the partitioned graph")
+    ego_local = ego_local.contiguous()
+    row_off = pg.rank * pg.rows_per_rank
+    st = _lib.stream_ptr()
+    _lib.check(L.fr_push_rows(ego_local.data_ptr(), pg.rows_per_rank, d, tables.peers[0], tables.world, row_off, st),
+               "fr_push_rows")
+    tables.barrier()
+    inv = 1.0 / (n_layers + 1)
+    out = None
+    for layer in range(n_layers):
+        x_full = tables.table(layer % 2)
+        if layer == n_layers - 1:
+            out = ops.spmm(g, x_full, Z=ego_local, alpha=inv, beta=inv)
+        else:
+            _lib.check(L.fr_spmm_csr_f32_push(
+                g.seg.data_ptr(), g.n_seg, g.long_rows.data_ptr(), g.n_long, g.col.data_ptr(), g.val.data_ptr(), d,
+                x_full.data_ptr(), ego_local.data_ptr(), 1.0, 1.0, None, g.partial(d).data_ptr(), g.counters.data_ptr(),
+                tables.peers[(layer + 1) % 2], tables.world, row_off, st), "fr_spmm_csr_f32_push")
+        tables.barrier()
+    return out
+
+
+class _PushedPropagate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ego_local, pg, n_layers, tables):
+        ctx.pg, ctx.n_layers, ctx.tables = pg, n_layers, tables
+        return propagate_mean_pushed_raw(pg, ego_local, n_layers, tables)
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.pg.symmetric:
+            raise RuntimeError("row-partitioned backward needs a symmetric graph (S^T = S)")
+        return propagate_mean_pushed_raw(ctx.pg, g.contiguous(), ctx.n_layers, ctx.tables), None, None, None
+
+
+def propagate_mean_pushed(pg: RowPartitionedGraph, ego_local: torch.Tensor, n_layers: int, tables: PeerTables):
+    """Differentiable row-partitioned layer-mean propagation over peer memory (no all-gather)."""
+    return _PushedPropagate.apply(ego_local, pg, n_layers, tables)
 
 
 # ------------------------------------------------------------------------------------ evaluation

@@ -658,7 +658,7 @@ static int spmm_entry(const int32_t *seg, int64_t n_seg, const int32_t *long_row
     FR_REQUIRE((((uintptr_t)X0 | (uintptr_t)X1 | (uintptr_t)Y | (uintptr_t)Z0 | (uintptr_t)Z1 | (uintptr_t)bias |
                  (uintptr_t)partial | (uintptr_t)seg | (uintptr_t)long_rows) & 15) == 0,
                "fr_spmm_csr_f32: pointers must be 16-byte aligned");
-    FR_REQUIRE(X0 != Y && X1 != Y, "fr_spmm_csr_f32: in-place propagation is not supported");
+    FR_REQUIRE(Y == nullptr || (X0 != Y && X1 != Y), "fr_spmm_csr_f32: in-place propagation is not supported");
     FR_REQUIRE(x_split >= 0 && z_split >= 0 && (X1 != nullptr || x_split == 0) && (Z1 == nullptr || Z0 != nullptr),
                "fr_spmm_csr_f32_split: bad split arguments");
     Split sp;

@@ -117,10 +117,13 @@ class _DevicePtr:
 
 
 class PeerTables:
-    """Two full-size `[n_padded, d]` fp32 tables on every rank of the node, each mapped into every other
-    rank with CUDA IPC (`fr_peer_alloc` / `fr_peer_open`).  `peers[b]` is the ctypes array of table b's
-    address on ranks 0..world-1 (this rank's own copy included), the destination list of the push
-    epilogue; `table(b)` views this rank's copy."""
+    """Four full-size `[n_padded, d]` fp32 tables on every rank of the node (two per call, calls
+    alternate between the two pairs), each mapped into every other rank with CUDA IPC (`fr_peer_alloc` /
+    `fr_peer_open`).  `peers[b]` is the ctypes array of table b's address on ranks 0..world-1 (this
+    rank's own copy included), the destination list of the push epilogue; `table(b)` views this rank's
+    copy.  Alternating pairs make an end-of-call barrier unnecessary: a rank can only start writing
+    pair A again after every rank has passed the barriers of the call that used pair B, i.e. after every
+    rank has finished reading pair A."""
 
     def __init__(self, n_padded: int, d: int, device, group=None):
         import ctypes as C
@@ -131,7 +134,7 @@ class PeerTables:
             raise _lib.FoodRecError("peer tables span one node: at most 8 ranks")
         self.n_padded, self.d, self.device = n_padded, d, torch.device(device)
         self.own, handles = [], []
-        for _ in range(2):
+        for _ in range(4):
             ptr, h = C.c_void_p(), C.create_string_buffer(64)
             _lib.check(_lib.lib.fr_peer_alloc(n_padded * d * 4, C.byref(ptr), h), "fr_peer_alloc")
             self.own.append(ptr.value)
@@ -139,7 +142,7 @@ class PeerTables:
         everyone = [None] * self.world
         dist.all_gather_object(everyone, handles, group=group)
         self.opened, self.peers = [], []
-        for b in range(2):
+        for b in range(4):
             addrs = []
             for q in range(self.world):
                 if q == self.rank:
@@ -152,7 +155,13 @@ class PeerTables:
             self.peers.append((C.c_void_p * self.world)(*addrs))
         self._views = [torch.as_tensor(_DevicePtr(p, n_padded, d), device=self.device) for p in self.own]
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._calls = 0
         self.barrier()
+
+    def next_pair(self) -> int:
+        """First table index of the pair the next propagation call uses (ranks call in lockstep)."""
+        self._calls += 1
+        return 2 * (self._calls & 1)
 
     def table(self, b: int) -> torch.Tensor:
         return self._views[b]
@@ -180,7 +189,7 @@ def propagate_mean_pushed_raw(pg: RowPartitionedGraph, ego_local: torch.Tensor, 
     """`mean_l S^l ego` for this rank's rows with the per-layer exchange fused into the producing kernel:
     layer l's epilogue stores its output rows into table (l+1) % 2 of every rank (`fr_spmm_csr_f32_push`),
     so there is no all-gather; the layer-0 input is exchanged by `fr_push_rows`.  A 4-byte all-reduce orders
-    the ranks after every exchange and at the end of the call (table reuse by the next call)."""
+    the ranks after every exchange (L per call)."""
     from . import _lib, ops
     L = _lib.lib
     if n_layers == 0:
@@ -191,22 +200,21 @@ def propagate_mean_pushed_raw(pg: RowPartitionedGraph, ego_local: torch.Tensor, 
     ego_local = ego_local.contiguous()
     row_off = pg.rank * pg.rows_per_rank
     st = _lib.stream_ptr()
-    _lib.check(L.fr_push_rows(ego_local.data_ptr(), pg.rows_per_rank, d, tables.peers[0], tables.world, row_off, st),
+    base = tables.next_pair()
+    _lib.check(L.fr_push_rows(ego_local.data_ptr(), pg.rows_per_rank, d, tables.peers[base], tables.world, row_off, st),
                "fr_push_rows")
     tables.barrier()
     inv = 1.0 / (n_layers + 1)
-    out = None
     for layer in range(n_layers):
-        x_full = tables.table(layer % 2)
+        x_full = tables.table(base + layer % 2)
         if layer == n_layers - 1:
-            out = ops.spmm(g, x_full, Z=ego_local, alpha=inv, beta=inv)
+            return ops.spmm(g, x_full, Z=ego_local, alpha=inv, beta=inv)
         else:
             _lib.check(L.fr_spmm_csr_f32_push(
                 g.seg.data_ptr(), g.n_seg, g.long_rows.data_ptr(), g.n_long, g.col.data_ptr(), g.val.data_ptr(), d,
                 x_full.data_ptr(), ego_local.data_ptr(), 1.0, 1.0, None, g.partial(d).data_ptr(), g.counters.data_ptr(),
-                tables.peers[(layer + 1) % 2], tables.world, row_off, st), "fr_spmm_csr_f32_push")
-        tables.barrier()
-    return out
+                tables.peers[base + (layer + 1) % 2], tables.world, row_off, st), "fr_spmm_csr_f32_push")
+            tables.barrier()
 
 
 class _PushedPropagate(torch.autograd.Function):

@@ -192,3 +192,37 @@ def test_row_masks_do_not_change_model_gradients(mini_ds, mini_batches):
     for n in grads[True]:
         a, b = grads[True][n], grads[False][n]
         assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max()) + 1e-12, n
+
+
+def test_push_epilogue_single_rank_matches_plain_propagation(mini_ds):
+    """World-size-1 run of the peer-memory path (`fr_peer_alloc`, `fr_push_rows`, `fr_spmm_csr_f32_push`): the
+    pushed copies feed the next layer, so the result must be bit-identical to `propagate_mean`, forward and
+    backward, across repeated calls (alternating table pairs).  Multi-rank runs: scripts/dist_propagation_check.py."""
+    import os
+    import torch.distributed as dist
+    from foodrec_b200 import dist as D, graph as G, ops
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        g = G.norm_adj_user_item(mini_ds.train_coo_matrix, mini_ds.n_users, mini_ds.n_items, "cuda")
+        pg = D.RowPartitionedGraph.from_graph(g, 0, 1, "cuda")
+        tables = D.PeerTables(pg.n_padded, 64, "cuda")
+        torch.manual_seed(3)
+        ego = torch.randn(g.n_rows, 64, device="cuda") * 0.1
+        w = torch.randn(g.n_rows, 64, device="cuda")
+        for layers in (1, 2, 3):
+            a = ego.clone().requires_grad_(True)
+            b = ego.clone().requires_grad_(True)
+            ref = ops.propagate_mean(g, a, layers)
+            (ref * w).sum().backward()
+            got = D.propagate_mean_pushed(pg, b, layers, tables)
+            (got * w).sum().backward()
+            assert torch.equal(got, ref), layers
+            assert torch.equal(b.grad, a.grad), layers
+        tables.close()
+    finally:
+        if created:
+            dist.destroy_process_group()

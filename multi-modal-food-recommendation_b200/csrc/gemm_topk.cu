@@ -472,6 +472,7 @@ struct Params2 {
     float *lv;   // [grid][BM][4][CAPG]
     int *li;
     int two_pass;
+    int bstride;   // the bounding sweep visits every bstride-th column tile (a subset still bounds from below)
 };
 
 template <bool AFFINE>   // AFFINE: scores are scale * acc + bias[col]; the plain instantiation carries none of that code
@@ -491,6 +492,7 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_mblk = (P.M + BM - 1) / BM, n_nblk = (P.N + BN - 1) / BN, n_kblk = (P.K + BK - 1) / BK;
     const int n_pass = PP.two_pass ? 2 : 1;
+    const int bstride = PP.bstride;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -514,7 +516,7 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t phase = 0;
             for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x)
               for (int pass = 0; pass < n_pass; ++pass)
-                for (int nb = 0; nb < n_nblk; ++nb)
+                for (int nb = 0; nb < n_nblk; nb += (n_pass == 2 && pass == 0) ? bstride : 1)
                     for (int kb = 0; kb < n_kblk; ++kb) {
                         mbar_wait(empty + stage, phase ^ 1);
                         uint8_t *a = tiles + stage * STAGE_BYTES, *b = a + A_BYTES;
@@ -529,7 +531,7 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t phase = 0, aphase = 0;
         for (int mb = blockIdx.x; mb < n_mblk; mb += gridDim.x)
           for (int pass = 0; pass < n_pass; ++pass)
-            for (int nb = 0; nb < n_nblk; ++nb) {
+            for (int nb = 0; nb < n_nblk; nb += (n_pass == 2 && pass == 0) ? bstride : 1) {
                 if (lane == 0) mbar_wait(tempty + as, aphase ^ 1);
                 __syncwarp();
                 tc_fence_after();
@@ -574,13 +576,17 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (n_pass == 2) {
                 // ---------------- pass 0: group maxima -> lower bound of the k-th eligible score
                 float gmax = -INFINITY;
-                // group id of (tile nb, quarter q) = floor((4 nb + q) NG / (4 n_nblk)), advanced incrementally:
-                // num = (4 nb + q) NG - gid * den stays in [0, den) (no per-tile 64-bit division)
-                const long long den = 4LL * n_nblk;
+                // Only every bstride-th column tile is visited: the (k + h)-th largest group maximum of a SUBSET of
+                // the columns is still a lower bound of the k-th eligible score over all of them -- a looser one
+                // (about bstride x more scores reach the candidate path of the collection sweep, still a vanishing
+                // fraction), for 1 / bstride of the bounding work.
+                // group id of (visited tile i, quarter q) = floor((4 i + q) NG / (4 n_vis)), advanced incrementally:
+                // num = (4 i + q) NG - gid * den stays in [0, den) (no per-tile 64-bit division)
+                const long long den = 4LL * ((n_nblk + bstride - 1) / bstride);
                 int gid = (int)(((long long)q * NG) / den);
                 long long num = (long long)q * NG - (long long)gid * den;
                 int gcur = gid;
-                for (int nb = 0; nb < n_nblk; ++nb) {
+                for (int nb = 0; nb < n_nblk; nb += bstride) {
                     if (lane == 0) mbar_wait(tfull + as, aphase);
                     __syncwarp();
                     tc_fence_after();
@@ -625,7 +631,7 @@ gemm_topk_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty + as);
                     if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
-                    num += 4LL * NG;                      // next tile: (4 (nb + 1) + q) NG
+                    num += 4LL * NG;                      // next visited tile: (4 (i + 1) + q) NG
                     while (num >= den) { num -= den; ++gid; }
                 }
                 if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
@@ -953,8 +959,18 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
             two_pass_env = e ? atoi(e) : -1;
         }
         const int two_pass = two_pass_env >= 0 ? two_pass_env : (K <= 256 ? 1 : 0);
+        // bounding sweep on a subset of the column tiles, keeping >= 32 tiles (4 x 32 = NG distinct groups)
+        static int bstride_env = -2;
+        if (bstride_env == -2) {
+            const char *e = getenv("FR_TOPK_BOUND_STRIDE");
+            bstride_env = e ? atoi(e) : -1;
+        }
+        const int n_nblk_h = (int)((N + BN - 1) / BN);
+        // measured at 200 000 x 500 000, k = 32: stride 1 / 2 / 4 / 8 = 36.8 / 32.8 / 35.7 / 45.7 ms (a looser bound sends
+        // more 32-score chunks down the divergent candidate path); at 45 000 columns stride 1 is best
+        const int bstride = std::max(1, std::min(bstride_env > 0 ? bstride_env : (n_nblk_h >= 1024 ? 2 : 1), n_nblk_h / 32));
         Params2 P2{P, reinterpret_cast<float *>(ws),
-                   reinterpret_cast<int *>(reinterpret_cast<float *>(ws) + (size_t)grid * BM * 4 * CAPG), two_pass};
+                   reinterpret_cast<int *>(reinterpret_cast<float *>(ws) + (size_t)grid * BM * 4 * CAPG), two_pass, bstride};
         fr::LaunchTimer _lt2("gemm_topk_kernel_v2", (cudaStream_t)stream);
         if (bias != nullptr || scale != 1.f)
             gemm_topk_kernel_v2<true><<<grid, THREADS2, SMEM2, (cudaStream_t)stream>>>(ma, mb, P2);

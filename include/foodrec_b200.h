@@ -264,6 +264,12 @@ int fr_spmm_csr_f32_push(const int32_t *seg, int64_t n_seg, const int32_t *long_
                          float beta, float *Y, float *partial, int32_t *counters, float *const *peers_host,
                          int32_t n_peers, int64_t row_off, void *stream);
 
+/* Measurement probe (not on the product path): gathers `n_idx` rows of a d = 64 table and does nothing else;
+ * its bytes/s is the gather roofline the propagation kernel is compared with (scripts/microbench_gather_roofline.py).
+ * out: blocks * 32 floats of scratch. */
+int fr_probe_gather(const float *tab, int32_t d, const int32_t *idx, int64_t n_idx, int32_t inflight, int32_t blocks,
+                    float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,11 +149,17 @@ def full_sort_topk(user_all: torch.Tensor, item_all: torch.Tensor, users: torch.
 
 def evaluate_full_sort(model, eval_users, pos_items, topk=(5, 10, 20, 50), metrics=("recall", "ndcg", "precision", "map"),
                        hist: HistoryCSR | None = None, batch_users: int = 65536):
-    """`Trainer.evaluate` for the dot-product models: propagate once, rank every eval user against
-    all items on the tensor cores, score with the reference's metric definitions."""
+    """`Trainer.evaluate` (FoodRec/common/trainer.py:476-503): rank every eval user against all items and
+    score with the reference's metric definitions.  Dot-product models propagate once and rank on the
+    tensor cores; a model with its own `full_sort_topk` (SCHGN: fused pair scorer) is asked directly."""
     from . import metrics as M
     model.eval()
     with torch.no_grad():
+        if hasattr(model, "full_sort_topk"):
+            dev = next(model.parameters()).device
+            users = torch.as_tensor(np.asarray(eval_users), device=dev)
+            top = model.full_sort_topk(users, max(topk), hist=hist)[1].cpu().numpy()
+            return M.topk_metrics(top, pos_items, metrics=metrics, topk=topk), top
         user_all, item_all = model._tables()
         users = torch.as_tensor(np.asarray(eval_users), device=user_all.device)
         tops = []

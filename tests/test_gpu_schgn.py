@@ -121,6 +121,25 @@ def test_c1_full_sort_matches_oracle_and_topk_with_mask(c1_model):
     assert torch.equal(i2, torch.topk(m.full_sort_scores(users), k).indices)
 
 
+def test_c1_evaluate_full_sort_metrics_match_oracle_ranking(c1_model):
+    """`evaluation.evaluate_full_sort` on SCHGN (the reference's `Trainer.evaluate` loop, no mask): Recall /
+    NDCG / Precision / MAP @5/10/20/50 over 64 users equal those of the CPU restatement's ranking to 4 d.p."""
+    from foodrec_b200 import evaluation, metrics as M
+    from oracle import schgn as O
+    m, ds = c1_model
+    users = list(range(0, 5000, 79))[:64]
+    pos = [ds.testRatings[u] for u in users]
+    got, top = evaluation.evaluate_full_sort(m, users, pos)
+    P = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ei = O.schgn_edge_index(ds)
+    sizes = (ds.n_users, ds.n_items, ds.num_ingredients, ds.num_calories_level)
+    ref_top = np.stack([torch.topk(O.full_sort_scores(P, ds, u, ei, sizes), 50).indices.numpy() for u in users[:16]])
+    want = M.topk_metrics(ref_top, pos[:16])
+    have = M.topk_metrics(top[:16], pos[:16])
+    assert have == want, (have, want)
+    assert set(got) == set(want)
+
+
 def test_c1_training_step_matches_oracle(c1_model, no_dropout):
     """One `calculate_loss` + backward at C1 scale against the CPU restatement (dropout = identity)."""
     from foodrec_b200.synth import sample_train_batches

@@ -299,6 +299,8 @@ def main():
     # same plan and operand shapes, bracketed by one CUDA-event pair on the launch stream: the stream stays
     # busy, so the figure is kernel time, not Python launch latency.  Operands stay L2-warm, as inside the step.
     tot_ms, tot_bytes, n_launch, REP = 0.0, 0.0, len(prof), 20
+    probe_ms, gathered = 0.0, 0.0          # the same launches' row gathers alone (`fr_probe_gather`): the gather roofline
+    probe_out = torch.empty(148 * 32 * 32, device=dev)
     bufs = {}
     for _, _, nb, g, has_z in prof:
         key = (g.n_rows, g.n_cols)
@@ -315,6 +317,14 @@ def main():
         torch.cuda.synchronize()
         tot_ms += a.elapsed_time(b) / REP
         tot_bytes += nb
+        a.record()
+        for _ in range(REP):
+            _lib.check(_lib.lib.fr_probe_gather(X.data_ptr(), 64, g.col.data_ptr(), g.nnz, 8, 148 * 32,
+                                                probe_out.data_ptr(), _lib.stream_ptr()), "fr_probe_gather")
+        b.record()
+        torch.cuda.synchronize()
+        probe_ms += a.elapsed_time(b) / REP
+        gathered += g.nnz * 256.0
     del bufs
     peaks = _peaks()
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
@@ -353,7 +363,14 @@ def main():
                                        "the step's tables stay in the 126 MB L2)",
                      "algorithmic_bytes_per_launch": tot_bytes / max(n_launch, 1),
                      "launches_per_step": n_launch / 3, "avg_launch_us": tot_ms * 1e3 / max(n_launch, 1),
-                     "kernel_share_of_step": tot_ms / 3 / ms_dev},
+                     "kernel_share_of_step": tot_ms / 3 / ms_dev,
+                     "gather_bound": {
+                         "note": "the tables are L2-resident at this scale, so the binding resource is the 256-byte row "
+                                 "gather (L1/L2 -> SM), not HBM: `fr_probe_gather` issues only the gathers of the same "
+                                 "launches (same column indices, nothing else) and is the ceiling for any gather-based SpMM",
+                         "gathered_GBs_in_kernel": gathered / (tot_ms * 1e-3) / 1e9,
+                         "gather_only_probe_GBs": gathered / (probe_ms * 1e-3) / 1e9,
+                         "kernel_time_over_gather_only_time": tot_ms / probe_ms, "frac_of_gather_roofline": probe_ms / tot_ms}},
     }
     tpeak = _tensor_peak()
     n_eval = ev["n_users"]

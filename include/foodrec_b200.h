@@ -270,6 +270,15 @@ int fr_spmm_csr_f32_push(const int32_t *seg, int64_t n_seg, const int32_t *long_
 int fr_probe_gather(const float *tab, int32_t d, const int32_t *idx, int64_t n_idx, int32_t inflight, int32_t blocks,
                     float *out, void *stream);
 
+/* Negative sampling on the device: out_neg[i] = an item drawn uniformly from the items NOT in users[i]'s sorted
+ * exclusion list (CSR over users: training + validation/test items).  Replaces the per-sample python rejection loop
+ * `TrainDataLoader.get_random_neg` (FoodRec/utils/dataloader.py:145-151).  Counter-based generator: the result is a
+ * pure function of (seed, step, i); same distribution as the reference, not numpy's stream.  *fail_count is
+ * incremented for a sample whose user excludes (almost) everything (4096 rejected draws); the caller checks it. */
+int fr_sample_negatives(const int64_t *excl_ptr, const int32_t *excl_idx, const int64_t *users, int64_t n,
+                        int32_t n_items, uint64_t seed, uint64_t step, int64_t *out_neg, int32_t *fail_count,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

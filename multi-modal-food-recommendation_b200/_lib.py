@@ -69,6 +69,7 @@ SIGNATURES = {
     "fr_push_rows": (C.c_int, [_p, _i64, _i32, _p, _i32, _i64, _p]),
     "fr_spmm_csr_f32_push": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i32, _p, _p, _f32, _f32, _p, _p, _p, _p, _i32, _i64, _p]),
     "fr_probe_gather": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p]),
+    "fr_sample_negatives": (C.c_int, [_p, _p, _p, _i64, _i32, C.c_uint64, C.c_uint64, _p, _p, _p]),
     "fr_schgn_attend": (C.c_int, [_p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "fr_schgn_score": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p]),
 }

@@ -102,3 +102,63 @@ class GraphedTrainStep:
             self.static[k].copy_(batch[k], non_blocking=True)
         self.graph.replay()
         return self.losses
+
+
+class DeviceBatchSampler:
+    """Training batches assembled on the device: a shuffled pass over the training interactions with one
+    uniformly drawn negative per sample (`fr_sample_negatives`), as `TrainDataLoader` + `DataLoader(shuffle=True)`
+    produce them (FoodRec/utils/dataloader.py:50-77,145-151) -- without the per-sample python rejection loop and
+    without a host round trip.  Negatives avoid the user's training items and, when the dataset carries them,
+    their validation / test items (`validRatings`, `testRatings`), like the reference.  Same distribution, a
+    different random stream: parity is statistical."""
+
+    def __init__(self, dataset, batch_size: int, device, seed: int = 0, drop_last: bool = False):
+        import numpy as np
+        coo = dataset.train_coo_matrix
+        self.n_items, self.batch_size, self.device = int(dataset.n_items), int(batch_size), torch.device(device)
+        u = np.asarray(coo.row, dtype=np.int64)
+        i = np.asarray(coo.col, dtype=np.int64)
+        self.users = torch.from_numpy(u).to(self.device)
+        self.items = torch.from_numpy(i).to(self.device)
+        eu, ei = [u], [i]
+        for name in ("validRatings", "testRatings"):
+            lists = getattr(dataset, name, None)
+            if lists is not None:
+                lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
+                eu.append(np.repeat(np.arange(len(lists), dtype=np.int64), lens))
+                ei.append(np.fromiter((j for x in lists for j in x), dtype=np.int64, count=int(lens.sum())))
+        keys = np.unique(np.concatenate(eu) * self.n_items + np.concatenate(ei))
+        ptr = np.zeros(int(dataset.n_users) + 1, dtype=np.int64)
+        np.cumsum(np.bincount(keys // self.n_items, minlength=int(dataset.n_users)), out=ptr[1:])
+        self.excl_ptr = torch.from_numpy(ptr).to(self.device)
+        self.excl_idx = torch.from_numpy((keys % self.n_items).astype(np.int32)).to(self.device)
+        self.seed, self.drop_last, self._step = int(seed), drop_last, 0
+        self._fail = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(self.seed)
+
+    def __len__(self):
+        n = self.users.numel()
+        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+
+    def negatives(self, users: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+        users = users.to(self.device, torch.int64).contiguous()
+        out = torch.empty_like(users)
+        self._step += 1
+        _lib.check(_lib.lib.fr_sample_negatives(
+            self.excl_ptr.data_ptr(), self.excl_idx.data_ptr(), users.data_ptr(), users.numel(), self.n_items,
+            self.seed & (2 ** 64 - 1), self._step, out.data_ptr(), self._fail.data_ptr(), _lib.stream_ptr()),
+            "fr_sample_negatives")
+        return out
+
+    def failures(self) -> int:
+        """Samples that found no admissible item so far (a user who interacted with almost every item)."""
+        return int(self._fail.item())
+
+    def __iter__(self):
+        perm = torch.randperm(self.users.numel(), device=self.device, generator=self._gen)
+        for b in range(len(self)):
+            sel = perm[b * self.batch_size:(b + 1) * self.batch_size]
+            u = self.users[sel]
+            yield {"u_id": u, "pos_i_id": self.items[sel], "neg_i_id": self.negatives(u)}

@@ -73,3 +73,41 @@ def test_graph_replay_step_equals_eager_step():
     for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         diff = (p1 - p2).abs()   # fp32 atomics order differs run to run; Adam turns that into rare +-lr moves
         assert float((diff > 2e-5).float().mean()) < 0.01, (n1, float((diff > 2e-5).float().mean()))
+
+
+def test_device_sampler_negatives_are_admissible_uniform_and_reproducible(mini_ds):
+    """`fr_sample_negatives` / `DeviceBatchSampler` (dataloader.py:145-151): a negative is never one of the
+    user's train / valid / test items, an epoch visits every interaction once, the draw is a pure function of
+    (seed, step), and over many draws the admissible items of a user are hit uniformly."""
+    from foodrec_b200.train import DeviceBatchSampler
+    ds = mini_ds
+    s = DeviceBatchSampler(ds, 64, "cuda", seed=5)
+    excl = [set() for _ in range(ds.n_users)]
+    for u, i in zip(ds.train_coo_matrix.row.tolist(), ds.train_coo_matrix.col.tolist()):
+        excl[u].add(i)
+    for u in range(ds.n_users):
+        excl[u].update(ds.validRatings[u])
+        excl[u].update(ds.testRatings[u])
+    seen = []
+    for batch in s:
+        u, p, n = (batch[k].cpu().numpy() for k in ("u_id", "pos_i_id", "neg_i_id"))
+        assert ((n >= 0) & (n < ds.n_items)).all()
+        assert not any(int(nn) in excl[int(uu)] for uu, nn in zip(u, n))
+        seen.append(u.astype(np.int64) * ds.n_items + p)
+    seen = np.sort(np.concatenate(seen))
+    want = np.sort(ds.train_coo_matrix.row.astype(np.int64) * ds.n_items + ds.train_coo_matrix.col)
+    assert np.array_equal(seen, want) and len(s) == -(-len(want) // 64)
+    assert s.failures() == 0
+    # reproducible: same seed => same epoch
+    a = [b["neg_i_id"].clone() for b in DeviceBatchSampler(ds, 64, "cuda", seed=9)]
+    b = [b["neg_i_id"].clone() for b in DeviceBatchSampler(ds, 64, "cuda", seed=9)]
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    # uniform over the admissible items of one user: chi-square against the flat distribution
+    user = 3
+    draws = torch.cat([s.negatives(torch.full((4096,), user, device="cuda")) for _ in range(8)]).cpu().numpy()
+    ok = np.array([i for i in range(ds.n_items) if i not in excl[user]])
+    counts = np.bincount(draws, minlength=ds.n_items)[ok]
+    assert counts.sum() == draws.size
+    expect = draws.size / ok.size
+    chi2 = ((counts - expect) ** 2 / expect).sum()
+    assert chi2 < ok.size + 6 * np.sqrt(2 * ok.size), (chi2, ok.size)

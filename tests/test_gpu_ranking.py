@@ -157,3 +157,26 @@ def test_wide_inner_dimension_single_sweep():
     val, ind = E.knn_topk(feat.cuda(), 10)
     xn = feat / feat.norm(dim=-1, keepdim=True)
     check_topk(val, ind, xn @ xn.t(), 10, atol=5e-6)
+
+
+def test_minibatch_kmeans_matches_sklearn_quality():
+    """`kmeans.minibatch_kmeans` (dataset_process/*_kmeans.ipynb cell 0) against scikit-learn's MiniBatchKMeans
+    on the same blobs: the inertia is within 10 % (different random stream: statistical parity), every point's
+    assignment is its exact nearest centre, and a second fit with the same seed lands on the same quality (the
+    per-centre sums are fp32 atomics, so the centres themselves may differ in the last bits)."""
+    from sklearn.cluster import MiniBatchKMeans
+    from foodrec_b200 import kmeans
+    rng = np.random.default_rng(0)
+    true = rng.standard_normal((24, 32)).astype(np.float32) * 3
+    x = (true[rng.integers(0, 24, 6000)] + rng.standard_normal((6000, 32)).astype(np.float32) * 0.6).astype(np.float32)
+    ref = MiniBatchKMeans(n_clusters=24, init_size=512, batch_size=256, random_state=2024, n_init=1).fit(x)
+    xt = torch.from_numpy(x).cuda()
+    centres, inertia = kmeans.minibatch_kmeans(xt, 24, batch_size=256, init_size=512, seed=2024)
+    assert centres.shape == (24, 32)
+    assert inertia <= 1.10 * ref.inertia_, (inertia, ref.inertia_)
+    idx, dist = kmeans.assign(xt, centres)
+    exact = torch.cdist(xt, centres).pow(2)
+    assert float((dist - exact.min(1).values).abs().max()) <= 1e-3
+    assert float((exact.gather(1, idx[:, None])[:, 0] - exact.min(1).values).abs().max()) <= 1e-4 * float(exact.max())
+    c2, i2 = kmeans.minibatch_kmeans(xt, 24, batch_size=256, init_size=512, seed=2024)
+    assert abs(i2 - inertia) <= 0.02 * inertia

@@ -169,3 +169,17 @@ def test_masked_ingredient_task_shapes(mini_ds):
     for r, c in zip(*np.nonzero(hidden)):
         assert b["neg_ingre_seq"][r, c] not in set(b["pos_ingre_code"][r, :b["pos_ingre_num"][r]])
     assert b["pos_img"].dtype == np.float64
+
+
+def test_public_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "foodrec_b200.h")
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)     # declarations only (comments cite torch call sites)
+    assert "torch" not in code.lower() and "at::" not in code and "std::" not in code

@@ -107,6 +107,61 @@ def propagate_mean_partitioned(pg: RowPartitionedGraph, ego_local: torch.Tensor,
     return _PartitionedPropagate.apply(ego_local, pg, n_layers, spmm or _device_spmm, group)
 
 
+# ----------------------------------------------------------------------- row-partitioned training step
+class _GatherRowsAutograd(torch.autograd.Function):
+    """`all_gather` of row blocks whose backward is the matching reduce-scatter (sum over ranks): every rank
+    reads rows of the full table for its own mini-batch, the row's owner receives the summed gradient."""
+
+    @staticmethod
+    def forward(ctx, x_local, group):
+        ctx.group, ctx.rows = group, x_local.shape[0]
+        return _all_gather_rows(x_local, group)
+
+    @staticmethod
+    def backward(ctx, g_full):
+        g_full = g_full.contiguous()
+        out = torch.empty((ctx.rows, g_full.shape[1]), dtype=g_full.dtype, device=g_full.device)
+        if dist.get_backend(ctx.group) == "gloo":          # gloo has no reduce-scatter: all-reduce and slice
+            dist.all_reduce(g_full, group=ctx.group)
+            r = dist.get_rank(ctx.group)
+            out.copy_(g_full[r * ctx.rows:(r + 1) * ctx.rows])
+        else:
+            dist.reduce_scatter_tensor(out, g_full, op=dist.ReduceOp.SUM, group=ctx.group)
+        return out, None
+
+
+def gather_rows_autograd(x_local: torch.Tensor, group=None) -> torch.Tensor:
+    return _GatherRowsAutograd.apply(x_local, group)
+
+
+def partitioned_bpr_losses(pg: RowPartitionedGraph, ego_local: torch.Tensor, n_users: int, n_layers: int, batch: dict,
+                           reg_weight: float, group=None, spmm=None, loss_fn=None, propagate=None):
+    """One data-parallel training step's losses on a ROW-PARTITIONED embedding table (the
+    LightGCN / CLUSSL user-item tower at graphs too large for one GPU): this rank owns `ego_local`
+    (`[rows_per_rank, d]`, users first then items in the global numbering) and a mini-batch of global ids.
+
+      propagate (one exchange per layer, row-local layer mean)            -> out_local
+      all-gather out_local and ego_local once (backward: reduce-scatter)   -> full tables for the batch gathers
+      BPR on the propagated rows + EmbLoss on the ego rows of THIS rank's batch (`fr_rank_loss_*`)
+
+    Returns `(mf_loss, reg_loss)` of this rank's batch; the caller backpropagates `sum(losses) / world`, which
+    makes the parameter gradient the mean over ranks -- the same semantics as the replicated data-parallel
+    step of `bench.py` (`train.OverlappedGradAllReduce`).  `loss_fn(full, ego_full, u, p, n)` and `spmm` are
+    injectable for the CPU (gloo) tests."""
+    propagate = propagate or (lambda e: propagate_mean_partitioned(pg, e, n_layers, group, spmm))
+    out_local = propagate(ego_local)
+    full = gather_rows_autograd(out_local, group)[:pg.n_nodes]
+    ego_full = gather_rows_autograd(ego_local, group)[:pg.n_nodes]
+    u, p, n = batch["u_id"], batch["pos_i_id"], batch["neg_i_id"]
+    if loss_fn is not None:
+        return loss_fn(full, ego_full, u, p, n)
+    from . import ops
+    mf, reg = ops.rank_loss(full.contiguous(), n_users, u, p, n,
+                            [(ego_full.contiguous(), u, None), (ego_full.contiguous(), p + n_users, None),
+                             (ego_full.contiguous(), n + n_users, None)], float(u.numel()))
+    return mf, reg_weight * reg
+
+
 # ------------------------------------------------------- propagation with the exchange fused into the kernel
 class _DevicePtr:
     """Raw device allocation exposed through `__cuda_array_interface__` so torch can view it."""

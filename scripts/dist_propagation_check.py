@@ -68,12 +68,45 @@ def main():
         o = D.propagate_mean_pushed(pg, ep, layers, tables)
         (o * o).sum().backward()
     t_gather, t_push = timed(step), timed(step_push)
+
+    # row-partitioned data-parallel training step (per-rank mini-batches, all-gather forward / reduce-scatter
+    # backward around the fused BPR + EmbLoss kernel) against the same step computed on one GPU
+    from foodrec_b200.synth import sample_train_batches
+    hb = sample_train_batches(ds, 512, world, seed=4)
+    batches = [{k: torch.from_numpy(b[k]).to(dev) for k in ("u_id", "pos_i_id", "neg_i_id")} for b in hb]
+    pe = pg.local_rows(ego).requires_grad_(True)
+    losses = D.partitioned_bpr_losses(pg, pe, ds.n_users, layers, batches[rank], 0.1)
+    (sum(losses) / world).backward()
+    e2 = ego.clone().requires_grad_(True)
+    full = ops.propagate_mean(g, e2, layers)
+    tot, mine = 0.0, None
+    for r, b in enumerate(batches):
+        mf, reg = ops.rank_loss(full, ds.n_users, b["u_id"], b["pos_i_id"], b["neg_i_id"],
+                                [(e2, b["u_id"], None), (e2, b["pos_i_id"] + ds.n_users, None),
+                                 (e2, b["neg_i_id"] + ds.n_users, None)], 512.0)
+        if r == rank:
+            mine = (float(mf), 0.1 * float(reg))
+        tot = tot + (mf + 0.1 * reg) / world
+    tot.backward()
+    gref = e2.grad[pg.lo:pg.hi]
+    err_l = max(abs(float(losses[0]) - mine[0]) / abs(mine[0]), abs(float(losses[1]) - mine[1]) / abs(mine[1]))
+    err_g = float((pe.grad[:n] - gref).abs().max() / gref.abs().max())
+    train_ok = torch.tensor([float(err_l < 1e-5 and err_g < 1e-5)], device=dev)
+    dist.all_reduce(train_ok, op=dist.ReduceOp.MIN)
+
+    def train_step():
+        pe.grad = None
+        ls = D.partitioned_bpr_losses(pg, pe, ds.n_users, layers, batches[rank], 0.1)
+        (sum(ls) / world).backward()
+    t_train = timed(train_step)
     if rank == 0:
         print(json.dumps({"world": world, "scale": scale, "layers": layers, "N": g.n_rows, "nnz": g.nnz,
                           "rel_err_fwd": err_f, "rel_err_bwd": err_b, "all_ranks_ok": bool(ok.item()),
                           "fwd_bwd_ms_max_over_ranks": t_gather,
                           "push_bit_identical_to_all_gather_path": bool(push_same.item()),
-                          "push_fwd_bwd_ms_max_over_ranks": t_push}))
+                          "push_fwd_bwd_ms_max_over_ranks": t_push,
+                          "partitioned_train_step": {"loss_rel_err": err_l, "grad_rel_err": err_g,
+                                                     "all_ranks_ok": bool(train_ok.item()), "ms_max_over_ranks": t_train}}))
     tables.close()
     dist.destroy_process_group()
 

@@ -100,3 +100,65 @@ def test_shard_arithmetic():
     u = torch.arange(10)
     parts = [D.shard_users(u, r, 4) for r in range(4)]
     assert torch.equal(torch.cat(parts), u) and [p.numel() for p in parts] == [3, 3, 3, 1]
+
+
+def _host_losses(full, ego_full, u, p, n, n_users, reg_weight):
+    from oracle import losses
+    mf = losses.bpr_from_tables(full[:n_users], full[n_users:], u, p, n)
+    reg = losses.emb_loss(ego_full[u], ego_full[n_users + p], ego_full[n_users + n])
+    return mf, reg_weight * reg
+
+
+def _train_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from foodrec_b200 import dist as D, graph as G
+        from foodrec_b200.synth import make_dataset, sample_train_batches
+        ds = make_dataset("mini")
+        g = G.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items, "cpu")
+        pg = D.RowPartitionedGraph(g.row_ptr_host, g.col.numpy(), g.val.numpy(), g.n_rows, rank, world, "cpu",
+                                   graph_cls=HostGraph)
+        torch.manual_seed(0)
+        ego = torch.randn(g.n_rows, 64) * 0.1
+        ego_l = pg.local_rows(ego).requires_grad_(True)
+        b = sample_train_batches(ds, 48, world, seed=4)[rank]                  # every rank its own mini-batch
+        batch = {k: torch.from_numpy(b[k]) for k in ("u_id", "pos_i_id", "neg_i_id")}
+        losses = D.partitioned_bpr_losses(
+            pg, ego_l, ds.n_users, 2, batch, 0.1, spmm=host_spmm,
+            loss_fn=lambda full, ego_full, u, p, n: _host_losses(full, ego_full, u, p, n, ds.n_users, 0.1))
+        (sum(losses) / world).backward()
+        out[rank] = (pg.lo, pg.hi, [float(x) for x in losses], ego_l.grad[:pg.hi - pg.lo].clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partitioned_training_step_world2():
+    """Losses and the owner's parameter gradient of the row-partitioned data-parallel step (all-gather forward,
+    reduce-scatter backward, per-rank mini-batches) equal the single-process mean over the two batches."""
+    from foodrec_b200 import graph as G
+    from foodrec_b200.synth import make_dataset, sample_train_batches
+    from oracle import propagation
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_train_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    ds = make_dataset("mini")
+    g = G.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items, "cpu")
+    S = HostGraph(g.row_ptr_host, g.col.numpy(), g.val.numpy(), g.n_rows, "cpu").S
+    torch.manual_seed(0)
+    ego = (torch.randn(g.n_rows, 64) * 0.1).requires_grad_(True)
+    full = propagation.layer_mean_propagate(S, ego, 2)
+    total, per_rank = 0.0, []
+    for b in sample_train_batches(ds, 48, world, seed=4):
+        u, p, n = (torch.from_numpy(b[k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+        mf, reg = _host_losses(full, ego, u, p, n, ds.n_users, 0.1)
+        per_rank.append([float(mf), float(reg)])
+        total = total + (mf + reg) / world
+    total.backward()
+    covered = 0
+    for r in range(world):
+        lo, hi, losses, grad = out[r]
+        np.testing.assert_allclose(losses, per_rank[r], rtol=1e-5)
+        assert torch.allclose(grad, ego.grad[lo:hi], rtol=1e-4, atol=1e-8)
+        covered += hi - lo
+    assert covered == g.n_rows

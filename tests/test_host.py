@@ -183,3 +183,18 @@ def test_public_header_is_plain_c():
     assert res.returncode == 0, res.stderr
     code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)     # declarations only (comments cite torch call sites)
     assert "torch" not in code.lower() and "at::" not in code and "std::" not in code
+
+
+def test_device_sampler_exclusion_lists_host_side(mini_ds):
+    """Host part of `train.DeviceBatchSampler`: the per-user exclusion CSR is train + valid + test items, sorted,
+    duplicate-free (what `get_random_neg` tests against, dataloader.py:145-151); epoch length = ceil(n / B)."""
+    from foodrec_b200.train import DeviceBatchSampler
+    s = DeviceBatchSampler(mini_ds, 64, "cpu", seed=1)
+    ptr, idx = s.excl_ptr.numpy(), s.excl_idx.numpy()
+    coo = mini_ds.train_coo_matrix
+    for u in (0, 3, 100, mini_ds.n_users - 1):
+        want = set(coo.col[coo.row == u].tolist()) | set(mini_ds.validRatings[u]) | set(mini_ds.testRatings[u])
+        got = idx[ptr[u]:ptr[u + 1]]
+        assert (np.diff(got) > 0).all() and set(got.tolist()) == want
+    assert ptr[-1] == idx.shape[0] and len(s) == -(-coo.nnz // 64)
+    assert len(DeviceBatchSampler(mini_ds, 64, "cpu", drop_last=True)) == coo.nnz // 64

@@ -1,0 +1,3 @@
+"""`get_model('LightGCN')` (FoodRec/utils/utils.py:27-40) resolves here when `dropin/` precedes `FoodRec/` on sys.path."""
+from _foodrec_b200_path import foodrec_b200  # noqa: F401  (puts the repo root on sys.path)
+from foodrec_b200.models.lightgcn import LightGCN  # noqa: E402,F401

@@ -1,0 +1,3 @@
+"""`get_model('SCHGN')` (FoodRec/utils/utils.py:27-40) resolves here when `dropin/` precedes `FoodRec/` on sys.path."""
+from _foodrec_b200_path import foodrec_b200  # noqa: F401  (puts the repo root on sys.path)
+from foodrec_b200.models.schgn import SCHGN  # noqa: E402,F401

@@ -184,16 +184,31 @@ int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_
  *   `hist_idx[hist_ptr[u] .. hist_ptr[u+1])` (sorted ascending) are excluded -- MMRec's
  *   `scores[train items] = -inf`; the reference applies no mask = pass NULLs.
  *   out_val / out_idx [M, topk] (topk <= 64), descending, ties to the lower column, -1 / -inf padding.
- * fr_rescore_topk_f32 re-scores kc >= k bf16 candidates exactly in fp32 (A_f32 rows `a_rows[m]` or m)
- * and keeps the best k; out_idx int64 like `torch.topk`.  metric 1 ranks by exact squared distance. */
+ * fr_rescore_topk_f32 re-scores the kc >= k bf16 candidates exactly in fp32 (A_f32 rows `a_rows[m]` or m) and keeps
+ * the best k; out_idx is int64 (`idx64` != 0, like `torch.topk`) or int32.  metric 1 ranks by exact squared
+ * distance.  With `cert` != NULL it also writes a per-row CERTIFICATE: cert[m] = 1 iff no column outside the
+ * candidate set can belong to the fp32 top-k, i.e. fewer than kc eligible columns existed or
+ *   cand_val[m, kc-1] + |scale| (|a' - a| max|b'| + |a| max|b' - b| + K 2^-23 |a'| max|b'|)  <  (k-th best fp32 re-score)
+ * with a' = bf16(A_m), b' = bf16(B_n) (`cand_val` = the bf16-pass scores of the candidates, `bmax` = the two
+ * device floats {max_n |b'_n|, max_n |b'_n - B_n|} from fr_max_row_norm).  Rows with
+ * cert = 0 are re-ranked by the caller with a wider candidate set or by fr_exact_topk_f32.
+ * fr_exact_topk_f32 is the exact path for such rows: fp32 scores of rows A[a_rows[0..Mf)] against ALL N columns on
+ * the CUDA cores (scores_ws: Mf * N floats of scratch), optional history mask (`hist_rows[r]` = CSR row of result
+ * row r), radix select of the k best, ordered by (score desc, column asc); -1 / -inf padding. */
 int fr_f32_to_bf16(const float *x, void *y_bf16, int64_t rows, int32_t d, int32_t l2_normalise, void *stream);
 int64_t fr_gemm_topk_ws_bytes(int32_t M); /* caller-provided scratch (candidate lists, L2-resident) */
 int fr_gemm_topk_bf16(const void *A_bf16, int32_t M, const void *B_bf16, int32_t N, int32_t K, float scale,
                       const float *bias, const int64_t *row_ids, const int64_t *hist_ptr, const int32_t *hist_idx,
                       int32_t topk, float *out_val, int32_t *out_idx, void *ws, int64_t ws_bytes, void *stream);
+int fr_max_row_norm(const float *B, int64_t rows, int32_t d, float *out /* 2 device floats */, void *stream);
 int fr_rescore_topk_f32(const float *A, const int64_t *a_rows, const float *B, int32_t d, float scale,
                         const float *bias, int32_t metric /* 0: scale*a.b+bias, 1: -|a-b|^2 */, const int32_t *cand,
-                        int32_t kc, int32_t M, int32_t k, float *out_val, int64_t *out_idx, void *stream);
+                        const float *cand_val, int32_t kc, int32_t M, int32_t k, float *out_val, void *out_idx,
+                        int32_t idx64, const float *bmax, uint8_t *cert, void *stream);
+int fr_exact_topk_f32(const float *A, const int64_t *a_rows, int32_t Mf, const float *B, int32_t N, int32_t d,
+                      float scale, const float *bias, int32_t metric, const int64_t *hist_rows,
+                      const int64_t *hist_ptr, const int32_t *hist_idx, int32_t k, float *scores_ws, float *out_val,
+                      int64_t *out_idx, void *stream);
 
 /* Mean cosine similarity of dense rows A[i] with gathered rows T[idx[i]] (eps = 1e-8 on each norm):
  * HealthRec's knowledge-distillation term `1 - cosine_similarity(item_know, cat(pos_e, neg_e)).mean()`

@@ -5,10 +5,11 @@ Replaces `Trainer.evaluate`'s per-user `full_sort_predict` + `torch.topk`
 (FoodRec/common/trainer.py:476-503), the LATTICE kNN utilities (FoodRec/utils/utils.py:118-183) and
 the centroid-assignment loop of dataset_process/*_kmeans.ipynb.  Pipeline per call:
 fp32 -> bf16 operands, `fr_gemm_topk_bf16` keeps `kc = k + slack` candidates per row from the bf16
-tensor-core scores, `fr_rescore_topk_f32` re-scores those exactly in fp32 and keeps the best k, so
-the result equals an fp32 `topk` unless bf16 rounding displaced a true top-k item by more than
-`slack` ranks (bf16 score error ~ 2^-8 |u||i|; measured displacement <= 3 ranks on the synthetic
-scales, default slack 12).
+tensor-core scores, `fr_rescore_topk_f32` re-scores those exactly in fp32, keeps the best k and CERTIFIES
+each row: a dropped column's fp32 score is at most (smallest kept bf16 score) + |u' - u| max|i'| + |u| max|i' - i|
+(u', i' the bf16-rounded rows), and if that is below the k-th re-scored value the row's result is the fp32 top-k.  Rows that fail are re-ranked with 64
+candidates and, failing again, scored against every column in fp32 (`fr_exact_topk_f32`).  The result is the
+fp32 `topk` (ties to the lower column) for every row -- a guarantee, not a heuristic.
 """
 from __future__ import annotations
 
@@ -72,37 +73,11 @@ def to_bf16(x: torch.Tensor, l2_normalise: bool = False) -> torch.Tensor:
     return y
 
 
-def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, bias: torch.Tensor | None = None,
-              row_ids: torch.Tensor | None = None, hist: HistoryCSR | None = None, slack: int = 12,
-              exact: bool = True, metric: int = 0, A_bf16: torch.Tensor | None = None,
-              B_bf16: torch.Tensor | None = None):
-    """Row-wise top-k of `scale * A @ B.T + bias` (A `[M, K]`, B `[N, K]` fp32) -> (values `[M, k]`
-    fp32, indices `[M, k]` int64), descending.  `hist` + `row_ids` exclude each row's history columns.
-    `exact=False` returns the bf16-scored top-k without the fp32 re-score."""
-    if k < 1 or k > MAX_K:
-        raise _lib.FoodRecError(f"k={k} outside [1, {MAX_K}]")
-    if exact and k + slack > MAX_K and k < B.shape[0]:
-        raise _lib.FoodRecError(f"exact top-{k} needs k + slack <= {MAX_K} candidates (slack={slack}); "
-                                f"the reference's largest cut-off is 50")
-    M, K = A.shape
-    N = B.shape[0]
-    if K % 8 != 0:
-        raise _lib.FoodRecError(f"inner dimension {K} must be a multiple of 8")
-    dev = A.device
-    A = A.detach().float().contiguous()
-    B = B.detach().float().contiguous()
-    Ab = A_bf16 if A_bf16 is not None else to_bf16(A)
-    Bb = B_bf16 if B_bf16 is not None else to_bf16(B)
-    kc = min(MAX_K, k + slack, N) if exact else min(k, N)
-    kc = max(kc, min(k, N))
+def _bf16_candidates(Ab, Bb, M, N, K, kc, scale, bias, row_ids, hist):
+    """One launch of the fused tensor-core score + (mask) + top-`kc` kernel -> (bf16-pass scores, columns)."""
+    dev = Ab.device
     cand_v = torch.empty((M, kc), dtype=torch.float32, device=dev)
     cand_i = torch.empty((M, kc), dtype=torch.int32, device=dev)
-    if hist is not None:
-        if row_ids is None:
-            row_ids = torch.arange(M, device=dev)
-        row_ids = row_ids.to(torch.int64).contiguous()
-    if bias is not None:
-        bias = bias.detach().float().contiguous()
     ws = _workspace(dev, int(_L.fr_gemm_topk_ws_bytes(M)))
     prof = PROFILE
     if prof is not None:
@@ -117,14 +92,114 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
         prof.append((ev0, ev1, 2.0 * M * N * K))
-    if not exact:
-        return cand_v[:, :k], cand_i[:, :k].to(torch.int64)
-    kk = min(k, kc)
-    out_v = torch.empty((M, kk), dtype=torch.float32, device=dev)
-    out_i = torch.empty((M, kk), dtype=torch.int64, device=dev)
-    _lib.check(_L.fr_rescore_topk_f32(A.data_ptr(), None, B.data_ptr(), K, float(scale), _lib.ptr(bias), int(metric),
-                                      cand_i.data_ptr(), kc, M, kk, out_v.data_ptr(), out_i.data_ptr(),
+    return cand_v, cand_i
+
+
+def _rescore(A, a_rows, B, K, scale, bias, metric, cand_v, cand_i, k, index_dtype, bmax):
+    """fp32 re-score of the candidates -> (values, indices, certificate [M] uint8)."""
+    M, kc = cand_i.shape
+    dev = A.device
+    out_v = torch.empty((M, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((M, k), dtype=index_dtype, device=dev)
+    cert = torch.empty(M, dtype=torch.uint8, device=dev)
+    _lib.check(_L.fr_rescore_topk_f32(A.data_ptr(), _lib.ptr(a_rows), B.data_ptr(), K, float(scale), _lib.ptr(bias), int(metric),
+                                      cand_i.data_ptr(), cand_v.data_ptr(), kc, M, k, out_v.data_ptr(), out_i.data_ptr(),
+                                      int(index_dtype == torch.int64), bmax.data_ptr(), cert.data_ptr(),
                                       _lib.stream_ptr()), "fr_rescore_topk_f32")
+    return out_v, out_i, cert
+
+
+def max_row_norm(B: torch.Tensor) -> torch.Tensor:
+    """`[max_n |bf16(B_n)|, max_n |bf16(B_n) - B_n|]` as two device floats (the column factors of the
+    certificate's rounding-error bound)."""
+    out = torch.empty(2, dtype=torch.float32, device=B.device)
+    _lib.check(_L.fr_max_row_norm(B.data_ptr(), B.shape[0], B.shape[1], out.data_ptr(), _lib.stream_ptr()), "fr_max_row_norm")
+    return out
+
+
+def exact_topk_rows(A, rows, B, k, *, scale=1.0, bias=None, metric=0, row_ids=None, hist=None, max_ws_bytes=1 << 30):
+    """fp32 top-k of rows `A[rows]` against every row of B on the CUDA cores (`fr_exact_topk_f32`): the path for
+    rows whose certificate failed.  Returns (values `[len(rows), k]`, int64 indices)."""
+    dev, N, K = A.device, B.shape[0], B.shape[1]
+    rows = rows.to(torch.int64).contiguous()
+    n = rows.numel()
+    out_v = torch.empty((n, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((n, k), dtype=torch.int64, device=dev)
+    chunk = max(1, min(n, max_ws_bytes // (4 * N)))
+    ws = torch.empty(chunk * N, dtype=torch.float32, device=dev)
+    hrows = None
+    if hist is not None:
+        hrows = (row_ids[rows] if row_ids is not None else rows).to(torch.int64).contiguous()
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        _lib.check(_L.fr_exact_topk_f32(
+            A.data_ptr(), rows[s:].data_ptr(), m, B.data_ptr(), N, K, float(scale), _lib.ptr(bias), int(metric),
+            hrows[s:].data_ptr() if hrows is not None else None, hist.ptr.data_ptr() if hist is not None else None,
+            hist.idx.data_ptr() if hist is not None else None, k, ws.data_ptr(), out_v[s:].data_ptr(), out_i[s:].data_ptr(),
+            _lib.stream_ptr()), "fr_exact_topk_f32")
+    return out_v, out_i
+
+
+def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, bias: torch.Tensor | None = None,
+              row_ids: torch.Tensor | None = None, hist: HistoryCSR | None = None, slack: int = 12,
+              exact: bool = True, metric: int = 0, A_bf16: torch.Tensor | None = None,
+              B_bf16: torch.Tensor | None = None, index_dtype=torch.int64, b_max_norm: torch.Tensor | None = None,
+              stats: dict | None = None):
+    """Row-wise top-k of `scale * A @ B.T + bias` (A `[M, K]`, B `[N, K]` fp32) -> (values `[M, k]`
+    fp32, indices `[M, k]` `index_dtype`), descending.  `hist` + `row_ids` exclude each row's history columns.
+
+    `exact=True` (default) returns the fp32 top-k, ties to the lower column: candidates from the bf16
+    tensor-core pass are re-scored in fp32, every row is checked against the rounding-error certificate
+    (`fr_rescore_topk_f32`), rows that fail are re-ranked with the widest candidate set and, if they fail
+    again, scored exactly against every column (`fr_exact_topk_f32`).  `stats` (a dict) receives how many rows
+    took each path.  `exact=False` returns the bf16-scored top-k without re-score."""
+    if k < 1 or k > MAX_K:
+        raise _lib.FoodRecError(f"k={k} outside [1, {MAX_K}]")
+    if index_dtype not in (torch.int64, torch.int32):
+        raise _lib.FoodRecError("index_dtype must be torch.int64 or torch.int32")
+    M, K = A.shape
+    N = B.shape[0]
+    if K % 8 != 0:
+        raise _lib.FoodRecError(f"inner dimension {K} must be a multiple of 8")
+    dev = A.device
+    A = A.detach().float().contiguous()
+    B = B.detach().float().contiguous()
+    Ab = A_bf16 if A_bf16 is not None else to_bf16(A)
+    Bb = B_bf16 if B_bf16 is not None else to_bf16(B)
+    kk = min(k, N)
+    kc = min(MAX_K, kk + max(int(slack), 0), N) if exact else kk
+    if hist is not None:
+        if row_ids is None:
+            row_ids = torch.arange(M, device=dev)
+        row_ids = row_ids.to(torch.int64).contiguous()
+    if bias is not None:
+        bias = bias.detach().float().contiguous()
+    cand_v, cand_i = _bf16_candidates(Ab, Bb, M, N, K, kc, scale, bias, row_ids, hist)
+    if not exact:
+        return cand_v[:, :kk], cand_i[:, :kk].to(index_dtype)
+    bmax = b_max_norm if b_max_norm is not None else max_row_norm(B)
+    out_v, out_i, cert = _rescore(A, None, B, K, scale, bias, metric, cand_v, cand_i, kk, index_dtype, bmax)
+    n_bad = int((cert == 0).sum().item())       # 4-byte read-back; rows beyond the certificate are rare
+    n_wide = n_exact = 0
+    if n_bad:
+        bad = torch.nonzero(cert == 0).reshape(-1)
+        kc2 = min(MAX_K, N)
+        if kc2 > kc:       # second chance on the tensor cores: the widest candidate set for just these rows
+            n_wide = n_bad
+            A_bad = A[bad].contiguous()
+            rid_bad = row_ids[bad].contiguous() if hist is not None else None
+            cv2, ci2 = _bf16_candidates(to_bf16(A_bad), Bb, n_bad, N, K, kc2, scale, bias, rid_bad, hist)
+            v2, i2, cert2 = _rescore(A_bad, None, B, K, scale, bias, metric, cv2, ci2, kk, index_dtype, bmax)
+            out_v[bad] = v2
+            out_i[bad] = i2
+            bad = bad[cert2 == 0]
+        n_exact = int(bad.numel())
+        if n_exact:
+            v3, i3 = exact_topk_rows(A, bad, B, kk, scale=scale, bias=bias, metric=metric, row_ids=row_ids, hist=hist)
+            out_v[bad] = v3
+            out_i[bad] = i3.to(index_dtype)
+    if stats is not None:
+        stats.update(rows=M, kc=kc, uncertified=n_bad, widened=n_wide, exact_rows=n_exact)
     return out_v, out_i
 
 
@@ -162,11 +237,13 @@ def evaluate_full_sort(model, eval_users, pos_items, topk=(5, 10, 20, 50), metri
             return M.topk_metrics(top, pos_items, metrics=metrics, topk=topk), top
         user_all, item_all = model._tables()
         users = torch.as_tensor(np.asarray(eval_users), device=user_all.device)
+        item_bf16, bmax = to_bf16(item_all), max_row_norm(item_all.detach().float().contiguous())
         tops = []
-        for s in range(0, users.numel(), batch_users):
-            _, idx = full_sort_topk(user_all, item_all, users[s:s + batch_users], max(topk), hist=hist)
+        for s in range(0, users.numel(), batch_users):     # int32 indices: half the device->host bytes of int64
+            _, idx = full_sort_topk(user_all, item_all, users[s:s + batch_users], max(topk), hist=hist,
+                                    B_bf16=item_bf16, b_max_norm=bmax, index_dtype=torch.int32)
             tops.append(idx)
-        top = torch.cat(tops, 0).cpu().numpy()
+        top = torch.cat(tops, 0).cpu().numpy().astype(np.int64)
     return M.topk_metrics(top, pos_items, metrics=metrics, topk=topk), top
 
 

@@ -42,8 +42,11 @@ class PropGraph:
                    "fr_spmm_plan_fill")
         self.seg_host, self.long_rows_host = seg, lrows
         dev = self.device
-        self.col = torch.from_numpy(np.ascontiguousarray(col, dtype=np.int32)).to(dev)
-        self.val = torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(dev)
+        # payload: host arrays are uploaded once; device tensors (a graph assembled on the GPU) are adopted as they are
+        self.col = (col.to(dev, torch.int32).contiguous() if torch.is_tensor(col)
+                    else torch.from_numpy(np.ascontiguousarray(col, dtype=np.int32)).to(dev))
+        self.val = (val.to(dev, torch.float32).contiguous() if torch.is_tensor(val)
+                    else torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(dev))
         self.seg = torch.from_numpy(seg).to(dev)
         self.long_rows = torch.from_numpy(lrows).to(dev)
         self.counters = torch.zeros(max(self.n_long, 1), dtype=torch.int32, device=dev)
@@ -92,6 +95,26 @@ def symmetric_normalised(rows, cols, n, device) -> PropGraph:
     if row_ptr[-1] >= 2 ** 31:
         raise _lib.FoodRecError("graph has >= 2^31 stored entries; int32 CSR offsets would overflow")
     return PropGraph(row_ptr, c, _sym_norm_values(row_ptr, r, c), n, device, transpose="self")
+
+
+def symmetric_normalised_device(rows: torch.Tensor, cols: torch.Tensor, n: int) -> PropGraph:
+    """`symmetric_normalised` with the edge list already on the GPU (int64 tensors): de-duplication, degrees and
+    the `(deg + 1e-7)^-1/2` products (fp64, cast to fp32 -- the reference's arithmetic, cikm_model.py:136-180) run
+    as device ops and only the row pointers (4 (n + 1) bytes) visit the host for the segment plan.  Used for
+    graphs whose host-side construction would take minutes (C5, 400 M stored entries)."""
+    dev = rows.device
+    key = torch.unique(torch.cat([rows * n + cols, cols * n + rows]))           # sorted, duplicate-free
+    if key.numel() >= 2 ** 31:
+        raise _lib.FoodRecError("graph has >= 2^31 stored entries; int32 CSR offsets would overflow")
+    r = torch.div(key, n, rounding_mode="floor")
+    c = key - r * n
+    del key
+    deg = torch.bincount(r, minlength=n)
+    row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=row_ptr[1:])
+    d = (deg.to(torch.float64) + 1e-7).pow(-0.5)
+    val = ((d[r] * 1.0) * d[c]).to(torch.float32)
+    return PropGraph(row_ptr.cpu().numpy(), c.to(torch.int32), val, n, dev, transpose="self")
 
 
 def norm_adj_user_item(train_coo, n_users: int, n_items: int, device) -> PropGraph:

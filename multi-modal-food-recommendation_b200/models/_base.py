@@ -13,6 +13,19 @@ class DotProductRecommender(GeneralRecommender):
     for any number of users per batch.  Sub-classes implement `_propagate_all()`
     returning the propagated `[n_users + n_items, d]` table plus model-specific extras."""
 
+    def train(self, mode: bool = True):
+        """Every mode switch drops the cached evaluation tables: the trainer calls `model.train()` /
+        `model.eval()` once per epoch / evaluation (FoodRec/common/trainer.py:156,233,478), so a cache
+        can never outlive the parameters it was computed from."""
+        self._eval_cache = None
+        return super().train(mode)
+
+    def _param_stamp(self):
+        """Identity of the current parameter values.  `_version` / `data_ptr` see ATen updates only; a
+        CUDA-graph replay (`train.GraphedTrainStep`) changes the values without touching either, so the
+        step drivers also bump `_param_generation` (`train.mark_parameters_updated`)."""
+        return (getattr(self, "_param_generation", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     def _tables(self):
         """Propagated (user_all, item_all); cached across calls while in eval mode under no_grad
         and the parameters are unchanged (the reference's by-user / full-sort loops call the model
@@ -20,7 +33,7 @@ class DotProductRecommender(GeneralRecommender):
         if self.training or torch.is_grad_enabled():
             all_emb = self._propagate_all()[0]
             return all_emb[:self.n_users], all_emb[self.n_users:]
-        stamp = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        stamp = self._param_stamp()
         cache = getattr(self, "_eval_cache", None)
         if cache is None or cache[0] != stamp:
             all_emb = self._propagate_all()[0]

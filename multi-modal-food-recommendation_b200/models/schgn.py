@@ -230,7 +230,13 @@ class SCHGN(GeneralRecommender):
 
     # ------------------------------------------------------------------ full sort (fused kernels)
     def _stamp(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # `_param_generation` is bumped by the step drivers (`train.mark_parameters_updated`): a CUDA-graph
+        # replay updates the parameters without changing `data_ptr` / `_version`
+        return (getattr(self, "_param_generation", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def train(self, mode: bool = True):
+        self._eval_cache = None          # a mode switch never keeps user-independent tables of older parameters
+        return super().train(mode)
 
     def _cached_gcn(self):
         if torch.is_grad_enabled():

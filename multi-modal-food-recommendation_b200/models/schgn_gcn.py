@@ -51,12 +51,17 @@ class GraphConv(nn.Module):
     def plan(self, edge_index: torch.Tensor, n_nodes: int):
         """Normalised CSR (+ transpose) for `edge_index` `[2, E]` (row 0 = source, row 1 = target);
         cached per edge tensor."""
-        key = (edge_index.data_ptr(), int(edge_index.shape[1]), n_nodes)
-        g = self._plans.get(key)
-        if g is None:
-            ei = edge_index.detach().cpu().numpy()
-            g = G.gcn_normalised(ei[0], ei[1], n_nodes, self.conv1.bias.device)
-            self._plans[key] = g
+        key = (edge_index.data_ptr(), int(edge_index.shape[1]), n_nodes, edge_index._version)
+        hit = self._plans.get(key)
+        if hit is not None:
+            return hit[1]
+        ei = edge_index.detach().cpu().numpy()
+        g = G.gcn_normalised(ei[0], ei[1], n_nodes, self.conv1.bias.device)
+        # the entry holds the edge tensor itself: while it is cached its address cannot be handed to another
+        # edge list of the same size (a temporary built per call would otherwise alias a stale plan)
+        if len(self._plans) >= 4:
+            self._plans.pop(next(iter(self._plans)))
+        self._plans[key] = (edge_index, g)
         return g
 
     def forward(self, x, edge_index):

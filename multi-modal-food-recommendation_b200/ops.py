@@ -49,8 +49,18 @@ def _register_mask(t: torch.Tensor, mask: torch.Tensor):
 
 
 def _take_mask(t: torch.Tensor):
+    """Pop the row mask registered for gradient tensor `t`.  Autograd synchronises streams for the gradient
+    tensors it routes, but it never sees the masks: the consumer may run on another stream than the producer
+    (CLUSSL's item-side graphs back-propagate on side streams), so the mask is recorded on the consuming
+    stream -- the caching allocator then cannot hand its block back to the producer's stream while the
+    consumer's kernel is still queued."""
     hit = _ROW_MASKS.pop((t.data_ptr(), tuple(t.shape)), None)
-    return None if hit is None else hit[1]
+    if hit is None:
+        return None
+    mask = hit[1]
+    base = mask._base if mask._base is not None else mask
+    base.record_stream(torch.cuda.current_stream())
+    return mask
 
 
 def spmm_masked(graph: PropGraph, X, Z, alpha, beta, x_mask, want_mask: bool):
@@ -477,6 +487,28 @@ class _GradHolder:
         self.stream = None
         self.done = False
         self.consumed = False
+        self._armed = False
+
+    def arm(self):
+        """Queue the end-of-backward check once per backward pass.  The hand-over is only correct when BOTH
+        halves are differentiated in the same pass (`loss = mf + cl + reg` as the trainer does).  If only the
+        contrastive total was differentiated (`cl_loss.backward(retain_graph=True)`, `autograd.grad(cl_loss, ..)`)
+        its table gradients are still parked here when the pass ends: that is reported loudly instead of
+        silently returning zero gradients, and the state is reset so nothing leaks into a later pass."""
+        if self._armed:
+            return
+        self._armed = True
+
+        def _end_of_pass():
+            lost = self.done and not self.consumed
+            self.d_tabs = self.masks = self.stream = None
+            self.done = self.consumed = self._armed = False
+            if lost:
+                raise _lib.FoodRecError(
+                    "ops.item_views: the contrastive total was back-propagated without item_emb in the same backward "
+                    "pass, so its table gradients were not delivered. Differentiate the summed loss in one pass, or "
+                    "use ops.dcor_terms(...) for a stand-alone contrastive term.")
+        torch.autograd.Variable._execution_engine.queue_callback(_end_of_pass)
 
 
 class _DcorTotalInto(torch.autograd.Function):
@@ -493,6 +525,7 @@ class _DcorTotalInto(torch.autograd.Function):
         idx = ctx.saved_tensors[0]
         state, tabs = ctx.saved_tensors[1:5], ctx.saved_tensors[5:]
         h = ctx.holder
+        h.arm()
         d_tabs = [torch.zeros_like(t) for t in tabs]
         masks = None
         if USE_ROW_MASKS and not h.consumed:
@@ -520,6 +553,7 @@ class _SumRowsInto(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_item):
         h, d = ctx.holder, ctx.shapes[0][1]
+        h.arm()
         g_item = g_item.contiguous()
         rows = (C.c_int64 * len(ctx.shapes))(*[int(sh[0]) for sh in ctx.shapes])
         src_mask = _take_mask(g_item)

@@ -11,6 +11,15 @@ from __future__ import annotations
 import torch
 
 
+def mark_parameters_updated(model):
+    """Invalidate everything cached from the parameter values (propagated evaluation tables, SCHGN's
+    user-independent scorer tables).  Needed because a CUDA-graph replay rewrites the parameters in
+    place without going through ATen: neither `data_ptr` nor `_version` changes."""
+    model._param_generation = getattr(model, "_param_generation", 0) + 1
+    if getattr(model, "_eval_cache", None) is not None:
+        model._eval_cache = None
+
+
 def eager_step(model, optimizer, batch, grad_hook=None):
     optimizer.zero_grad()
     losses = model.calculate_loss(batch)
@@ -19,6 +28,7 @@ def eager_step(model, optimizer, batch, grad_hook=None):
     if grad_hook is not None:
         grad_hook(model)
     optimizer.step()
+    mark_parameters_updated(model)
     return losses
 
 
@@ -101,6 +111,7 @@ class GraphedTrainStep:
         for k in self.keys:
             self.static[k].copy_(batch[k], non_blocking=True)
         self.graph.replay()
+        mark_parameters_updated(self.model)
         return self.losses
 
 
@@ -109,7 +120,8 @@ class DeviceBatchSampler:
     uniformly drawn negative per sample (`fr_sample_negatives`), as `TrainDataLoader` + `DataLoader(shuffle=True)`
     produce them (FoodRec/utils/dataloader.py:50-77,145-151) -- without the per-sample python rejection loop and
     without a host round trip.  Negatives avoid the user's training items and, when the dataset carries them,
-    their validation / test items (`validRatings`, `testRatings`), like the reference.  Same distribution, a
+    their validation / test items (`validTestRatings`; else `validRatings` mapped through `valid_users`, and
+    `testRatings`), like the reference.  Same distribution, a
     different random stream: parity is statistical."""
 
     def __init__(self, dataset, batch_size: int, device, seed: int = 0, drop_last: bool = False):
@@ -121,11 +133,33 @@ class DeviceBatchSampler:
         self.users = torch.from_numpy(u).to(self.device)
         self.items = torch.from_numpy(i).to(self.device)
         eu, ei = [u], [i]
-        for name in ("validRatings", "testRatings"):
-            lists = getattr(dataset, name, None)
-            if lists is not None:
+        n_users = int(dataset.n_users)
+        vt = getattr(dataset, "validTestRatings", None)
+        if vt is not None:
+            # the reference's own exclusion structure: dict user -> set of held-out items
+            # (FoodRec/utils/dataset.py:35,93-113, read by utils/dataloader.py:145-151)
+            us = np.fromiter((uu for uu, items in vt.items() for _ in items), dtype=np.int64)
+            it = np.fromiter((j for items in vt.values() for j in items), dtype=np.int64)
+            eu.append(us)
+            ei.append(it)
+        else:
+            # `validRatings` is POSITIONAL in the reference (paired with `valid_users`: users without validation
+            # rows are skipped, dataset.py:32,115-135); `testRatings` has one list per user
+            for name, owners in (("validRatings", "valid_users"), ("testRatings", "test_users")):
+                lists = getattr(dataset, name, None)
+                if lists is None:
+                    continue
+                ids = getattr(dataset, owners, None)
+                if ids is None:
+                    if len(lists) != n_users:
+                        raise ValueError(f"dataset.{name} has {len(lists)} lists for {n_users} users and no "
+                                         f"dataset.{owners} to map them: cannot attribute held-out items")
+                    ids = np.arange(n_users, dtype=np.int64)
+                ids = np.asarray(ids, dtype=np.int64)
+                if ids.shape[0] != len(lists):
+                    raise ValueError(f"dataset.{owners} and dataset.{name} differ in length")
                 lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
-                eu.append(np.repeat(np.arange(len(lists), dtype=np.int64), lens))
+                eu.append(np.repeat(ids, lens))
                 ei.append(np.fromiter((j for x in lists for j in x), dtype=np.int64, count=int(lens.sum())))
         keys = np.unique(np.concatenate(eu) * self.n_items + np.concatenate(ei))
         ptr = np.zeros(int(dataset.n_users) + 1, dtype=np.int64)

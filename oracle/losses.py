@@ -11,7 +11,7 @@ def bpr_loss(pos_score, neg_score, gamma=1e-10):
 def emb_loss(*embs):
     """Un-squared Frobenius norms summed, divided by the LAST argument's leading extent.
     FoodRec/common/loss.py:45-50."""
-    tot = torch.zeros(1)
+    tot = torch.zeros(1, device=embs[0].device)      # the reference: `torch.zeros(1).to(embeddings[-1].device)`, loss.py:46
     for e in embs:
         tot = tot + torch.norm(e, p=2)
     return tot / embs[-1].shape[0]
@@ -26,7 +26,7 @@ def bpr_from_tables(user_all, item_all, u, p, n):
 
 def correlation_distance(x, y):
     """Distance correlation of two [n, d] views.  FoodRec/models/pricai_modelx.py:409-437."""
-    zero = torch.zeros(1)
+    zero = torch.zeros(1, device=x.device)           # pricai_modelx.py:410 `torch.zeros(1).to(self.device)`
 
     def centred(X):
         r = (X * X).sum(1, keepdim=True)
@@ -49,12 +49,12 @@ def info_nce(hidden, temperature=0.5, hidden_norm=True):
     if hidden_norm:
         hidden = F.normalize(hidden, p=2, dim=-1)
     h1, h2 = hidden[:b], hidden[b:2 * b]
-    eye = torch.eye(b) * 1e9
+    eye = torch.eye(b, device=hidden.device) * 1e9
     aa = h1 @ h1.t() / temperature - eye
     bb = h2 @ h2.t() / temperature - eye
     ab = h1 @ h2.t() / temperature
     ba = h2 @ h1.t() / temperature
-    lab = torch.arange(b)
+    lab = torch.arange(b, device=hidden.device)
     la = F.cross_entropy(torch.cat([ab, aa], 1), lab)
     lb = F.cross_entropy(torch.cat([ba, bb], 1), lab)
     return (la + lb) / b

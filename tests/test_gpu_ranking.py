@@ -146,7 +146,19 @@ def test_rejects_bad_shapes():
     with pytest.raises(_lib.FoodRecError):
         E.gemm_topk(torch.randn(4, 64).cuda(), torch.randn(9, 64).cuda(), 65)
     with pytest.raises(_lib.FoodRecError):
-        E.gemm_topk(torch.randn(4, 64).cuda(), torch.randn(900, 64).cuda(), 60)  # no room for bf16 slack
+        E.gemm_topk(torch.randn(4, 64).cuda(), torch.randn(9, 64).cuda(), 3, index_dtype=torch.int16)
+
+
+def test_k_near_the_candidate_capacity_is_still_exact():
+    """k = 60 leaves only 4 spare candidates: the certificate (not a slack heuristic) guarantees the result, rows it
+    cannot certify go through the exact fp32 kernel."""
+    from foodrec_b200 import evaluation as E
+    torch.manual_seed(8)
+    A, B = torch.randn(70, 64) * 0.1, torch.randn(900, 64) * 0.1
+    st = {}
+    val, idx = E.gemm_topk(A.cuda(), B.cuda(), 60, stats=st)
+    check_topk(val, idx, A @ B.t(), 60)
+    assert st["rows"] == 70 and st["kc"] == 64
 
 
 def test_wide_inner_dimension_single_sweep():
@@ -180,3 +192,119 @@ def test_minibatch_kmeans_matches_sklearn_quality():
     assert float((exact.gather(1, idx[:, None])[:, 0] - exact.min(1).values).abs().max()) <= 1e-4 * float(exact.max())
     c2, i2 = kmeans.minibatch_kmeans(xt, 24, batch_size=256, init_size=512, seed=2024)
     assert abs(i2 - inertia) <= 0.02 * inertia
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The paths that only large shapes reach (they ran only inside bench.py's spot checks): the bounding sweep
+# on every second column tile (N >= 262 144), the persistent loop over more row blocks than CTA pairs
+# (M > 148 * 128) and users whose history is longer than the NG = 128 group maxima of the bounding pass.
+def _sampled_reference(U, I, hist, rows, k):
+    S = (U[rows].double() @ I.double().t()).float().cpu()           # fp64 accumulate -> the fp32 ranking without summation noise
+    S32 = (U[rows] @ I.t()).cpu()
+    for r, u in enumerate(rows.tolist()):
+        if hist is not None:
+            cols = hist.idx_host[hist.ptr_host[u]:hist.ptr_host[u + 1]].astype(np.int64)
+            S[r, cols] = -float("inf")
+            S32[r, cols] = -float("inf")
+    return S, S32
+
+
+@pytest.mark.parametrize("k", [20, 50])
+def test_large_shape_two_sweep_persistent_long_history(k):
+    from foodrec_b200 import evaluation as E
+    import scipy.sparse as sp
+    dev = "cuda"
+    M, N, K = 20_000, 300_000, 64
+    g = torch.Generator(device=dev).manual_seed(1234 + k)
+    U = torch.randn(M, K, device=dev, generator=g) * 0.1
+    I = torch.randn(N, K, device=dev, generator=g) * 0.1
+    rng = np.random.default_rng(k)
+    deg = rng.integers(0, 40, size=M)
+    long_users = rng.choice(M, size=64, replace=False)
+    deg[long_users] = rng.integers(129, 700, size=64)                # history > NG: the bound falls back to -inf
+    rows = np.repeat(np.arange(M), deg)
+    cols = rng.integers(0, N, size=rows.size)
+    hist = E.HistoryCSR(sp.coo_matrix((np.ones(rows.size, np.float32), (rows, cols)), shape=(M, N)), M, dev)
+    st = {}
+    val, idx = E.gemm_topk(U, I, k, hist=hist, stats=st, index_dtype=torch.int32)
+    assert idx.dtype == torch.int32 and idx.shape == (M, k)
+    sample = torch.from_numpy(np.unique(np.concatenate([long_users, rng.choice(M, size=512, replace=False),
+                                                        np.arange(M - 130, M)]))).to(dev)
+    S, _ = _sampled_reference(U, I, hist, sample.cpu(), k)
+    check_topk(val[sample], idx[sample].long(), S, k, atol=3e-6)
+    for r, u in enumerate(sample.tolist()):                          # no masked item is ever returned
+        seen = set(hist.idx_host[hist.ptr_host[u]:hist.ptr_host[u + 1]].tolist())
+        assert not (set(idx[u].tolist()) & seen)
+    assert st["exact_rows"] <= st["uncertified"] <= M // 50          # the certificate passes for almost every row here
+
+
+def test_persistent_loop_more_row_blocks_than_ctas():
+    """M > 148 * 128 rows: every CTA pair walks several 256-row blocks (TMEM / barrier phases carry over)."""
+    from foodrec_b200 import evaluation as E
+    dev = "cuda"
+    M, N, K, k = 148 * 128 + 777, 4096, 64, 20
+    g = torch.Generator(device=dev).manual_seed(99)
+    U = torch.randn(M, K, device=dev, generator=g) * 0.1
+    I = torch.randn(N, K, device=dev, generator=g) * 0.1
+    val, idx = E.gemm_topk(U, I, k)
+    sample = torch.cat([torch.arange(0, M, 37, device=dev), torch.arange(M - 300, M, device=dev)])
+    check_topk(val[sample], idx[sample], (U[sample].double() @ I.double().t()).float().cpu(), k, atol=3e-6)
+
+
+def test_certificate_catches_adversarial_near_ties():
+    """Columns engineered so that bf16 rounding reorders them across the candidate cut: many near-duplicates of the
+    best items differ by less than bf16 resolution.  The bf16 pass alone cannot rank them; the certificate must flag
+    those rows and the fallback must still return the fp32 top-k."""
+    from foodrec_b200 import evaluation as E
+    torch.manual_seed(3)
+    M, N, K, k = 96, 6000, 64, 20
+    A = torch.randn(M, K) * 0.1
+    B = torch.randn(N, K) * 0.02
+    base = torch.randn(1, K) * 0.3
+    B[:200] = base + torch.randn(200, K) * 2e-4          # 200 columns within ~1e-4 of each other: far below 2^-8 relative
+    A[:48] = base * 0.5 + torch.randn(48, K) * 0.01      # rows that score that cluster highest
+    st = {}
+    val, idx = E.gemm_topk(A.cuda(), B.cuda(), k, stats=st)
+    S = (A.double() @ B.double().t()).float()
+    check_topk(val, idx, S, k, atol=4e-6)
+    assert st["uncertified"] >= 40 and st["exact_rows"] >= 40        # the adversarial rows were caught ...
+    ref_i = torch.topk(S, k, dim=-1)[1]
+    gap = (torch.topk(S, k + 1, dim=-1)[0][:, k - 1] - torch.topk(S, k + 1, dim=-1)[0][:, k]).abs()
+    clear = gap > 8e-6
+    assert torch.equal(torch.sort(idx.cpu()[clear], 1)[0], torch.sort(ref_i[clear], 1)[0])   # ... and answered exactly
+    raw_v, raw_i = E.gemm_topk(A.cuda(), B.cuda(), k, exact=False)                            # the bf16 pass alone is wrong here
+    assert not torch.equal(torch.sort(raw_i.cpu()[:48], 1)[0], torch.sort(ref_i[:48], 1)[0])
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_exact_fp32_row_kernel(metric):
+    """`fr_exact_topk_f32` on its own: arbitrary row subset, history mask, ties to the lower column, padding."""
+    from foodrec_b200 import evaluation as E
+    import scipy.sparse as sp
+    torch.manual_seed(21)
+    M, N, K, k = 50, 3001, 72, 33
+    A, B = torch.randn(M, K), torch.randn(N, K)
+    B[100] = B[7]                                         # exact duplicates: the lower column must come first
+    B[2000] = B[7]
+    rows = torch.tensor([3, 49, 0, 17, 17, 8])
+    rng = np.random.default_rng(5)
+    hr = np.repeat(np.arange(M), 30)
+    hc = rng.integers(0, N, size=hr.size)
+    hist = E.HistoryCSR(sp.coo_matrix((np.ones(hr.size, np.float32), (hr, hc)), shape=(M, N)), M, "cuda")
+    bias = torch.randn(N) if metric == 0 else None
+    v, i = E.exact_topk_rows(A.cuda(), rows.cuda(), B.cuda(), k, scale=0.5 if metric == 0 else 1.0,
+                             bias=None if bias is None else bias.cuda(), metric=metric, hist=hist)
+    if metric == 0:
+        S = 0.5 * (A[rows].double() @ B.double().t()).float() + bias
+    else:
+        S = -(torch.cdist(A[rows].double(), B.double()) ** 2).float()
+    for r, u in enumerate(rows.tolist()):
+        S[r, hist.idx_host[hist.ptr_host[u]:hist.ptr_host[u + 1]].astype(np.int64)] = -float("inf")
+    check_topk(v, i, S, k, atol=2e-4 if metric else 2e-5)
+    i = i.cpu()
+    for r in range(rows.numel()):
+        pos = {c: int((i[r] == c).nonzero()[0]) for c in (7, 100, 2000) if (i[r] == c).any()}
+        assert list(pos) == sorted(pos, key=pos.get)     # duplicates appear in ascending column order
+    # fewer eligible columns than k: padded with -1 / -inf
+    tiny_v, tiny_i = E.exact_topk_rows(A.cuda(), rows[:2].cuda(), B[:10].cuda(), 33, metric=metric)
+    assert tiny_i.shape == (2, 33) and int((tiny_i >= 0).sum()) == 20 and bool(torch.isinf(tiny_v[:, 10:]).all())

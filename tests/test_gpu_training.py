@@ -111,3 +111,102 @@ def test_device_sampler_negatives_are_admissible_uniform_and_reproducible(mini_d
     expect = draws.size / ok.size
     chi2 = ((counts - expect) ** 2 / expect).sum()
     assert chi2 < ok.size + 6 * np.sqrt(2 * ok.size), (chi2, ok.size)
+
+
+def test_evaluation_after_graph_replay_sees_the_new_parameters():
+    """a CUDA-graph replay updates the parameters without touching `data_ptr` / `_version`, so an
+    evaluation cache keyed on those froze the metrics after the first evaluation.  train(replay) -> eval ->
+    train(replay) -> eval must see different tables, and each must equal a fresh propagation."""
+    from foodrec_b200 import evaluation as E
+    from foodrec_b200.synth import make_dataset, sample_train_batches
+    from foodrec_b200.train import GraphedTrainStep
+    ds = make_dataset("mini")
+    m, _ = make(ds)
+    opt = torch.optim.Adam(m.parameters(), lr=0.01, capturable=True)
+    batches = sample_train_batches(ds, 64, 4, seed=2)
+    dev = [{k: torch.from_numpy(b[k]).cuda() for k in ("u_id", "pos_i_id", "neg_i_id")} for b in batches]
+    m.train()
+    step = GraphedTrainStep(m, opt, dev[0], warmup=1)
+    users = np.arange(ds.n_users)
+    tabs, tops = [], []
+    for rnd in range(3):
+        m.train()
+        for b in dev:
+            step(b)
+        res, top = E.evaluate_full_sort(m, users, ds.testRatings, topk=(10, 20), metrics=("recall", "ndcg"))
+        with torch.no_grad():
+            cached = m._tables()[0].clone()            # eval mode, no_grad: the cached path
+            m.train()
+            fresh = m.forward()[0].detach().clone()    # train mode: always a fresh propagation
+            m.eval()
+        assert torch.allclose(cached, fresh, rtol=1e-6, atol=1e-7), rnd
+        tabs.append(cached)
+        tops.append(top)
+        # a replay WITHOUT a mode switch must invalidate too (by-user loops call the model between steps)
+        before = m._tables()[0].clone()
+        step(dev[0])
+        with torch.no_grad():
+            after = m._tables()[0]
+        assert not torch.equal(before, after)
+    assert not torch.equal(tabs[0], tabs[1]) and not torch.equal(tabs[1], tabs[2])
+    assert (tops[0] != tops[2]).any()
+
+
+def test_row_masks_survive_cross_stream_backward():
+    """row-activity masks travel between autograd nodes outside autograd's stream bookkeeping
+    and are consumed on side streams.  Many iterations with forked streams, masks on vs off, must give bit-identical
+    gradients (a recycled mask block would silently drop gathers)."""
+    from foodrec_b200 import ops
+    from foodrec_b200.synth import make_dataset, sample_train_batches
+    ds = make_dataset("C1")
+    batches = sample_train_batches(ds, 512, 6, seed=13)
+    dev = [{k: torch.from_numpy(b[k]).cuda() for k in ("u_id", "pos_i_id", "neg_i_id")} for b in batches]
+    m, _ = make(ds)
+    m.train()
+    m.fork_streams = True
+    junk = []
+
+    def grads(b, use_masks):
+        ops.USE_ROW_MASKS = use_masks
+        m.zero_grad(set_to_none=True)
+        sum(m.calculate_loss(b)).backward()
+        # allocator pressure on the main stream right after the backward: would reuse a prematurely freed mask block
+        junk.append(torch.full((ds.n_items + ds.cfg.n_cluster,), 0, dtype=torch.uint8, device="cuda"))
+        return [p.grad.clone() for p in m.parameters() if p.grad is not None]
+    try:
+        for it in range(30):
+            b = dev[it % len(dev)]
+            ga, gb = grads(b, True), grads(b, False)
+            torch.cuda.synchronize()
+            for x, y in zip(ga, gb):
+                # dense-atomic accumulation order differs run to run in the loss kernels, not in the propagation:
+                # compare with the tolerance of fp32 atomics, and exactly where the gradient is structurally zero
+                assert torch.equal(x == 0, y == 0), it
+                assert torch.allclose(x, y, rtol=1e-5, atol=1e-9), it
+            junk.clear()
+    finally:
+        ops.USE_ROW_MASKS = True
+
+
+def test_item_views_refuses_a_split_backward():
+    """differentiating only the contrastive total (without item_emb in the same pass) used to park
+    its table gradients and silently return zeros.  It is now reported loudly, and the next regular step is clean."""
+    from foodrec_b200 import _lib
+    from foodrec_b200.synth import make_dataset, sample_train_batches
+    ds = make_dataset("mini")
+    m, _ = make(ds)
+    m.train()
+    b = {k: torch.from_numpy(v).cuda() for k, v in sample_train_batches(ds, 64, 1, seed=3)[0].items()
+         if k in ("u_id", "pos_i_id", "neg_i_id")}
+    mf, cl, reg = m.calculate_loss(b)
+    with pytest.raises((_lib.FoodRecError, RuntimeError)):
+        cl.sum().backward(retain_graph=True)
+    m.zero_grad(set_to_none=True)
+    mf, cl, reg = m.calculate_loss(b)
+    (mf + cl.sum() + reg.sum()).backward()
+    g1 = [p.grad.clone() for p in m.parameters() if p.grad is not None]
+    m.zero_grad(set_to_none=True)
+    mf, cl, reg = m.calculate_loss(b)
+    (mf + cl.sum() + reg.sum()).backward()
+    for x, y in zip(g1, [p.grad for p in m.parameters() if p.grad is not None]):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-9)

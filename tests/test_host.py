@@ -198,3 +198,72 @@ def test_device_sampler_exclusion_lists_host_side(mini_ds):
         assert (np.diff(got) > 0).all() and set(got.tolist()) == want
     assert ptr[-1] == idx.shape[0] and len(s) == -(-coo.nnz // 64)
     assert len(DeviceBatchSampler(mini_ds, 64, "cpu", drop_last=True)) == coo.nnz // 64
+
+
+def test_device_sampler_reference_shaped_heldout_structures(mini_ds):
+    """The reference's `validRatings` is positional (paired with `valid_users`; users without validation rows are
+    skipped, FoodRec/utils/dataset.py:32,115-135) and its sampler reads `validTestRatings` (dict user -> set,
+    dataset.py:35,93-113; dataloader.py:145-151).  Held-out items must land on the right users either way."""
+    import copy
+    from foodrec_b200.train import DeviceBatchSampler
+    ds = copy.copy(mini_ds)
+    keep = [u for u in range(ds.n_users) if u % 3 != 1]                 # a third of the users have no validation rows
+    ds.valid_users = np.asarray(keep)
+    ds.validRatings = [mini_ds.validRatings[u] for u in keep]
+    coo = ds.train_coo_matrix
+
+    def check(s):
+        ptr, idx = s.excl_ptr.numpy(), s.excl_idx.numpy()
+        for u in (0, 1, 2, 4, 100, ds.n_users - 1):
+            want = set(coo.col[coo.row == u].tolist()) | set(mini_ds.testRatings[u])
+            if u % 3 != 1:
+                want |= set(mini_ds.validRatings[u])
+            assert set(idx[ptr[u]:ptr[u + 1]].tolist()) == want, u
+    check(DeviceBatchSampler(ds, 64, "cpu"))
+    ds2 = copy.copy(ds)
+    ds2.validTestRatings = {u: set(mini_ds.testRatings[u]) | (set(mini_ds.validRatings[u]) if u % 3 != 1 else set())
+                            for u in range(ds.n_users)}
+    ds2.validRatings = ds2.testRatings = None                           # the dict alone must be enough
+    check(DeviceBatchSampler(ds2, 64, "cpu"))
+    ds3 = copy.copy(ds)
+    ds3.valid_users = None                                              # positional lists without owners: refuse to guess
+    with pytest.raises(ValueError):
+        DeviceBatchSampler(ds3, 64, "cpu")
+
+
+def test_device_graph_builder_matches_host_builder():
+    """`graph.symmetric_normalised_device` (torch ops, used for the C5-shaped stress graph) reproduces the host
+    builder bit for bit (same de-duplication, fp64 degree products cast to fp32)."""
+    rng = np.random.default_rng(3)
+    u, i = rng.integers(0, 300, 5000), rng.integers(300, 420, 5000)
+    a = G.symmetric_normalised(u, i, 420, "cpu")
+    b = G.symmetric_normalised_device(torch.from_numpy(u), torch.from_numpy(i), 420)
+    assert np.array_equal(a.row_ptr_host, b.row_ptr_host) and torch.equal(a.col, b.col) and torch.equal(a.val, b.val)
+    assert np.array_equal(a.seg_host, b.seg_host)
+
+
+REFERENCE = "/root/reference/FoodRec"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference checkout only exists in the build container")
+def test_unmodified_get_model_resolves_the_dropins():
+    """Zero-edit discovery: with `dropin/` ahead of `FoodRec/` on sys.path the reference's own
+    `get_model` (FoodRec/utils/utils.py:27-40) returns the B200 classes for the four hot-path models and still finds
+    the reference's other models through the overlay's `__path__`."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, types\n"
+        f"sys.path[:0] = [{os.path.join(ROOT, 'dropin')!r}, {REFERENCE!r}, {os.path.dirname(REFERENCE)!r}]\n"   # bm3.py imports `FoodRec.common...`
+        "from utils.utils import get_model\n"
+        "for name, mod in (('PRICAI_ModelX', 'pricai_modelx'), ('CIKM_Model', 'cikm_model'), ('LightGCN', 'lightgcn'), ('SCHGN', 'schgn')):\n"
+        "    cls = get_model(name)\n"
+        "    import foodrec_b200, importlib\n"
+        "    want = getattr(importlib.import_module('foodrec_b200.models.' + mod), name)\n"
+        "    assert cls is want, (name, cls, want)\n"
+        "    assert 'multi-modal-food-recommendation_b200' in sys.modules[cls.__module__].__file__\n"
+        "bm3 = get_model('BM3')\n"                       # not overridden: the reference's own file
+        f"assert sys.modules[bm3.__module__].__file__.startswith({REFERENCE!r}), sys.modules[bm3.__module__].__file__\n"
+        "print('ok')\n")
+    res = subprocess.run([sys.executable, "-c", code], cwd=REFERENCE, capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stderr[-2000:]

@@ -64,8 +64,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Arrive on an mbarrier of (possibly) the other CTA of the pair.  Default semantics (release at CTA scope): the TMEM
+// reads it orders are already complete (`tcgen05.wait::ld` + `tcgen05.fence::before_thread_sync`); a
+// `.release.cluster` arrive compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, which was a third of all
+// stall samples of the epilogue warps (profiles/r2_rank_pair_probe_*).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose bytes complete on an mbarrier of (possibly) the other CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *dst, int c0, int c1) {
@@ -88,16 +92,34 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3)
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&r)[64]) {
+// asynchronous 32-lane x 32-column TMEM load: the registers are valid only after tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, float (&r)[32]) {
     uint32_t *u = reinterpret_cast<uint32_t *>(r);
-    // one instruction moves 32 lanes x 64 columns; the wait sits in the same asm block so that no use of r[] can be
-    // scheduled between the asynchronous load and its completion
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31]), "=r"(u[32]), "=r"(u[33]), "=r"(u[34]), "=r"(u[35]), "=r"(u[36]), "=r"(u[37]), "=r"(u[38]), "=r"(u[39]), "=r"(u[40]), "=r"(u[41]), "=r"(u[42]), "=r"(u[43]), "=r"(u[44]), "=r"(u[45]), "=r"(u[46]), "=r"(u[47]), "=r"(u[48]), "=r"(u[49]), "=r"(u[50]), "=r"(u[51]), "=r"(u[52]), "=r"(u[53]), "=r"(u[54]), "=r"(u[55]), "=r"(u[56]), "=r"(u[57]), "=r"(u[58]), "=r"(u[59]), "=r"(u[60]), "=r"(u[61]), "=r"(u[62]), "=r"(u[63])
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
         : "r"(taddr)
         : "memory");
+}
+// The wait names the loaded registers as in/out operands, so no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_wait_ld(float (&a)[32], float (&b)[32]) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(a), *w = reinterpret_cast<uint32_t *>(b);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]),
+                   "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15]), "+r"(u[16]),
+                   "+r"(u[17]), "+r"(u[18]), "+r"(u[19]), "+r"(u[20]), "+r"(u[21]), "+r"(u[22]), "+r"(u[23]), "+r"(u[24]),
+                   "+r"(u[25]), "+r"(u[26]), "+r"(u[27]), "+r"(u[28]), "+r"(u[29]), "+r"(u[30]), "+r"(u[31]),
+                   "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]),
+                   "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "+r"(w[16]),
+                   "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]), "+r"(w[21]), "+r"(w[22]), "+r"(w[23]), "+r"(w[24]),
+                   "+r"(w[25]), "+r"(w[26]), "+r"(w[27]), "+r"(w[28]), "+r"(w[29]), "+r"(w[30]), "+r"(w[31])
+                 :
+                 : "memory");
 }
 
 // kind::f16 instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
@@ -157,39 +179,91 @@ struct PairParams {
     int two_pass;
     int bstride;   // the bounding sweep visits every bstride-th column tile (a subset still bounds from below)
     int n_stages;  // depth of the operand ring
+    float thr0;    // initial threshold: -inf (debug: +inf measures the pipeline with no candidate ever taken)
     uint32_t off_ring, off_cnt, off_thr, off_gkey, off_bars;   // byte offsets inside the 1024-aligned dynamic shared memory
 };
 
-// scores of one (row, 64-column quarter): TMEM -> registers, optional affine map, columns >= N forced to -inf
-template <bool AFFINE, bool TAIL>
-__device__ __forceinline__ void load_scores(uint32_t taddr, float (&r)[64], const Params &P, int col0, int valid) {
-    tmem_ld64(taddr, r);
+// ---- epilogue helpers.  A thread owns (row, 64-column quarter of every tile) as two 32-column register halves
+// (576 threads put five warps on one SM sub-partition: <= 96 registers per thread).
+
+// optional affine map and tail handling of one half: columns >= N forced to -inf (they are zero-filled by TMA)
+template <bool AFFINE>
+__device__ __forceinline__ void fix_scores(float (&r)[32], const Params &P, int col0, int valid) {
     if (AFFINE) {
         if (P.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) r[j] = fmaf(r[j], P.scale, (!TAIL || j < valid) ? __ldg(P.bias + col0 + j) : 0.f);
+            for (int j = 0; j < 32; ++j) r[j] = fmaf(r[j], P.scale, j < valid ? __ldg(P.bias + col0 + j) : 0.f);
         } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) r[j] *= P.scale;
+            for (int j = 0; j < 32; ++j) r[j] *= P.scale;
         }
     }
-    if (TAIL) {
+    if (valid < 32) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j)
-            if (j >= valid) r[j] = -INFINITY;          // zero-filled columns past N must neither bound nor be collected
+        for (int j = 0; j < 32; ++j)
+            if (j >= valid) r[j] = -INFINITY;
     }
 }
 
-// maxima of the eight 8-column groups of a quarter
-__device__ __forceinline__ void group_max(const float (&r)[64], float (&g)[8]) {
+__device__ __forceinline__ float max8(const float (&r)[32], int g) {
+    return max3(max3(r[8 * g], r[8 * g + 1], r[8 * g + 2]), max3(r[8 * g + 3], r[8 * g + 4], r[8 * g + 5]),
+                fmaxf(r[8 * g + 6], r[8 * g + 7]));
+}
+__device__ __forceinline__ float max32(const float (&r)[32]) {
+    return fmaxf(max3(max8(r, 0), max8(r, 1), max8(r, 2)), max8(r, 3));
+}
+
+// History mask as a CURSOR over the row's sorted history slice: `h0` is the next history column not yet passed,
+// `h1` the one after it (loaded one event ahead, so the global-load latency is never waited for).  The common case is
+// one compare per 64 scores; a history column inside the current 64 columns poisons its register (-inf), so masked
+// scores never reach the bounds, the thresholds or the candidate lists (and no candidate needs a search).
+struct HistCursor {
+    const int32_t *base;
+    int n, pos, h0, h1;
+    __device__ __forceinline__ void reset() {
+        pos = 0;
+        h0 = n > 0 ? __ldg(base) : 0x7fffffff;
+        h1 = n > 1 ? __ldg(base + 1) : 0x7fffffff;
+    }
+    __device__ __forceinline__ void advance() {
+        h0 = h1;
+        ++pos;
+        h1 = pos + 1 < n ? __ldg(base + pos + 1) : 0x7fffffff;
+    }
+};
+__device__ __forceinline__ void poison(float (&r)[32], int d) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-        g[q] = max3(max3(r[8 * q], r[8 * q + 1], r[8 * q + 2]), max3(r[8 * q + 3], r[8 * q + 4], r[8 * q + 5]),
-                    fmaxf(r[8 * q + 6], r[8 * q + 7]));
+    for (int j = 0; j < 32; ++j) r[j] = j == d ? -INFINITY : r[j];
+}
+// all history columns < col0 + 64 are consumed; those inside [col0, col0 + 64) are poisoned
+__device__ __forceinline__ void apply_history(HistCursor &hc, float (&r0)[32], float (&r1)[32], int col0) {
+    while (hc.h0 < col0 + 64) {
+        const int d = hc.h0 - col0;
+        if (d >= 32) poison(r1, d - 32);
+        else if (d >= 0) poison(r0, d);
+        hc.advance();
+    }
+}
+
+// rare path: append every score above the threshold (8-column groups without one are skipped)
+__device__ __forceinline__ void collect(const float (&r)[32], int col0, float thr, float *lv, int *li, int &cnt) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (max8(r, g) > thr) {
+#pragma unroll
+            for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                if (r[j] > thr) {
+                    __stcg(lv + cnt, r[j]);
+                    __stcg(li + cnt, col0 + j);
+                    ++cnt;
+                }
+            }
+        }
+    }
 }
 
 template <bool AFFINE, bool ARES>   // AFFINE: scores are scale * acc + bias[col];  ARES: the A block stays resident (K <= 128)
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, PairParams PP) {
     const Params &P = PP.p;
     extern __shared__ uint8_t smem_raw[];
@@ -309,55 +383,64 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t tlane = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)q * 64;
         int as = 0;
         uint32_t aphase = 0;
+        // One visit of a tile: both halves of the quarter are loaded with one wait, the accumulator stage is handed back
+        // to the MMA issuer at once (the scores are in registers), then tails / affine map / history are applied.
+        auto load_tile = [&](float (&r0)[32], float (&r1)[32], int col0, HistCursor &hc) {
+            mbar_wait(tfull + as, aphase);
+            tc_fence_after();
+            tmem_ld32_async(tlane + as * BN, r0);
+            tmem_ld32_async(tlane + as * BN + 32, r1);
+            tmem_wait_ld(r0, r1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty0 + 8u * as);
+            if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+            const int valid = P.N - col0;
+            if (AFFINE || valid < 64) {
+                fix_scores<AFFINE>(r0, P, col0, min(32, valid));
+                fix_scores<AFFINE>(r1, P, col0 + 32, min(32, valid - 32));
+            }
+            if (hc.h0 < col0 + 64) apply_history(hc, r0, r1, col0);
+        };
         for (int sb = pair; sb < n_sblk; sb += n_pairs) {
             const int row_blk0 = sb * 2 * BM + (int)rank * BM;
             const int row = row_blk0 + r_in_blk;
-            float thr = -INFINITY;
+            float thr = PP.thr0;
             int cnt = 0;
-            long long hlo = 0, hhi = 0;
+            HistCursor hc{P.hist_idx, 0, 0, 0x7fffffff, 0x7fffffff};
             if (P.row_ids != nullptr && row < P.M) {
                 const long long id = P.row_ids[row];
-                hlo = P.hist_ptr[id];
-                hhi = P.hist_ptr[id + 1];
+                const long long hlo = P.hist_ptr[id];
+                hc.base = P.hist_idx + hlo;
+                hc.n = (int)(P.hist_ptr[id + 1] - hlo);
             }
             if (n_pass == 2) {
-                // ---------------- pass 0: group maxima -> lower bound of the k-th eligible score
+                // ---------------- pass 0: group maxima -> lower bound of the k-th eligible score (masked columns are
+                // poisoned before the maxima, so the k-th largest group maximum bounds the k-th ELIGIBLE score)
                 // group id of (visited tile i, quarter q) = floor((4 i + q) NG / (4 n_vis)), advanced incrementally:
                 // num = (4 i + q) NG - gid * den stays in [0, den)
+                hc.reset();
                 float gmax = -INFINITY;
                 const long long den = 4LL * ((n_nblk + bstride - 1) / bstride);
                 int gid = (int)(((long long)q * NG) / den);
                 long long num = (long long)q * NG - (long long)gid * den;
                 int gcur = gid;
                 for (int nb = 0; nb < n_nblk; nb += bstride) {
-                    mbar_wait(tfull + as, aphase);
-                    tc_fence_after();
+                    float r0[32], r1[32];
+                    load_tile(r0, r1, nb * BN + q * 64, hc);
                     if (gid != gcur) {
                         if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
                         gmax = -INFINITY;
                         gcur = gid;
                     }
-                    const int col0 = nb * BN + q * 64;
-                    const int valid = P.N - col0;
-                    if (valid > 0) {
-                        float r[64];
-                        if (valid >= 64) load_scores<AFFINE, false>(tlane + as * BN, r, P, col0, 64);
-                        else load_scores<AFFINE, true>(tlane + as * BN, r, P, col0, valid);
-                        float g[8];
-                        group_max(r, g);
-                        gmax = fmaxf(gmax, fmaxf(max3(g[0], g[1], g[2]), max3(g[3], g[4], max3(g[5], g[6], g[7]))));
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty0 + 8u * as);
-                    if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+                    gmax = max3(gmax, max32(r0), max32(r1));
                     num += 4LL * NG;                      // next visited tile: (4 (i + 1) + q) NG
                     while (num >= den) { num -= den; ++gid; }
                 }
                 if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
                 __threadfence_block();
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "r"(128) : "memory");
-                // warp q of the lane group bounds rows q*8 .. q*8+7: the (k + h)-th largest of NG group maxima
+                // warp q of the lane group bounds rows q*8 .. q*8+7: the k-th largest of NG group maxima
                 for (int rr = 0; rr < 8; ++rr) {
                     const int rib = lg * 32 + q * 8 + rr;
                     uint32_t key[NG / 32];
@@ -366,68 +449,36 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         key[t] = gkey[(lane + 32 * t) * BM + rib];
                         gkey[(lane + 32 * t) * BM + rib] = 0u;       // ready for the next row block
                     }
-                    int h = 0;
-                    const int orow = row_blk0 + rib;
-                    if (P.row_ids != nullptr && orow < P.M) {
-                        const long long id = P.row_ids[orow];
-                        const long long hl = P.hist_ptr[id + 1] - P.hist_ptr[id];
-                        h = hl > NG ? NG : (int)hl;
-                    }
-                    const int want = kk + h;
                     uint32_t Tk = 0;
-                    if (want <= NG) {
-                        for (int bit = 31; bit >= 0; --bit) {
-                            const uint32_t c = Tk | (1u << bit);
-                            int n = 0;
+                    for (int bit = 31; bit >= 0; --bit) {
+                        const uint32_t c = Tk | (1u << bit);
+                        int n = 0;
 #pragma unroll
-                            for (int t = 0; t < NG / 32; ++t) n += __popc(__ballot_sync(0xffffffffu, key[t] >= c));
-                            if (n >= want) Tk = c;
-                        }
+                        for (int t = 0; t < NG / 32; ++t) n += __popc(__ballot_sync(0xffffffffu, key[t] >= c));
+                        if (n >= kk) Tk = c;
                     }
                     // collection accepts `score > thr`: publish the key just below T so that ties with T pass
-                    if (lane == 0) thr_key[rib] = Tk > 1u ? Tk - 1u : 0u;
+                    // (key 0 = "no group", order_key(-inf) = 0x007fffff: fewer than k finite maxima give thr = -inf)
+                    if (lane == 0) thr_key[rib] = Tk > order_key(-INFINITY) ? Tk - 1u : 0u;
                 }
                 __threadfence_block();
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "r"(128) : "memory");
             }
             // -------------------- collection sweep
+            hc.reset();
             for (int nb = 0; nb < n_nblk; ++nb) {
-                mbar_wait(tfull + as, aphase);
-                tc_fence_after();
+                float r0[32], r1[32];
+                const int col0 = nb * BN + q * 64;
+                load_tile(r0, r1, col0, hc);
                 const uint32_t shared_key = thr_key[r_in_blk];
                 if (shared_key != 0u) thr = fmaxf(thr, key_value(shared_key));
-                const int col0 = nb * BN + q * 64;
-                const int valid = P.N - col0;
-                if (valid > 0) {
-                    float r[64];
-                    if (valid >= 64) load_scores<AFFINE, false>(tlane + as * BN, r, P, col0, 64);
-                    else load_scores<AFFINE, true>(tlane + as * BN, r, P, col0, valid);
-                    // hot path: 3-input max tree over eight 8-column groups, one compare per 64 scores
-                    float g[8];
-                    group_max(r, g);
-                    const float mx = fmaxf(max3(g[0], g[1], g[2]), max3(g[3], g[4], max3(g[5], g[6], g[7])));
-                    if (mx > thr) {
-                        // only the lanes (rows) that hold a candidate come here, and each walks only the 8-column
-                        // groups that hold one: the cost follows the number of candidates (-inf never passes)
-#pragma unroll
-                        for (int gq = 0; gq < 8; ++gq) {
-                            if (g[gq] > thr) {
-#pragma unroll
-                                for (int j = 8 * gq; j < 8 * gq + 8; ++j) {
-                                    if (r[j] > thr && (hlo == hhi || !in_history(P.hist_idx, hlo, hhi, col0 + j))) {
-                                        __stcg(lv + cnt, r[j]);
-                                        __stcg(li + cnt, col0 + j);
-                                        ++cnt;
-                                    }
-                                }
-                            }
-                        }
-                    }
+                // hot path: 3-input max trees, one compare per 64 scores
+                if (fmaxf(max32(r0), max32(r1)) > thr) {
+                    // only the lanes (rows) that hold a candidate come here, and each walks only the 8-column groups
+                    // that hold one: the cost follows the number of candidates (-inf never passes)
+                    collect(r0, col0, thr, lv, li, cnt);
+                    collect(r1, col0 + 32, thr, lv, li, cnt);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(tempty0 + 8u * as);     // the tile is in registers: release it first
-                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
                 // lists that could overflow on the next visit are pruned by the whole warp
                 uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 64);
                 if (need) { __threadfence_block(); __syncwarp(); }
@@ -697,7 +748,7 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
     FR_REQUIRE(ws != nullptr && ws_bytes >= need, "fr_gemm_topk_bf16: workspace of %lld bytes required (got %lld)",
                (long long)need, (long long)ws_bytes);
     PairParams PP{P, reinterpret_cast<float *>(ws), reinterpret_cast<int *>(reinterpret_cast<float *>(ws) + (size_t)L.grid * BM * 4 * CAP),
-                  two_pass, bstride, L.stages, L.off_ring, L.off_cnt, L.off_thr, L.off_gkey, L.off_bars};
+                  two_pass, bstride, L.stages, getenv("FR_TOPK_PROBE") ? INFINITY : -INFINITY, L.off_ring, L.off_cnt, L.off_thr, L.off_gkey, L.off_bars};
     const bool affine = bias != nullptr || scale != 1.f;
     if (affine) return L.ares ? launch_pair<true, true>(ma, mb, PP, L, st) : launch_pair<true, false>(ma, mb, PP, L, st);
     return L.ares ? launch_pair<false, true>(ma, mb, PP, L, st) : launch_pair<false, false>(ma, mb, PP, L, st);

@@ -235,7 +235,9 @@ def test_large_shape_two_sweep_persistent_long_history(k):
     for r, u in enumerate(sample.tolist()):                          # no masked item is ever returned
         seen = set(hist.idx_host[hist.ptr_host[u]:hist.ptr_host[u + 1]].tolist())
         assert not (set(idx[u].tolist()) & seen)
-    assert st["exact_rows"] <= st["uncertified"] <= M // 50          # the certificate passes for almost every row here
+    # the certificate passes for almost every row at k = 20; at k = 50 the widest candidate set (64) leaves only 14
+    # ranks of slack against a 2^-8 |u| max|i| rounding bound, so more rows take the wide / exact fp32 paths
+    assert st["exact_rows"] <= st["uncertified"] <= (M // 50 if k == 20 else M // 4)
 
 
 def test_persistent_loop_more_row_blocks_than_ctas():

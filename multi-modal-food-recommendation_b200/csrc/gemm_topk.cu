@@ -48,6 +48,8 @@ constexpr int NG = 128;                      // column groups per row for the bo
 constexpr int CAP = 128;                     // slots per (row, quarter) list; one visit appends <= 64, prune when > CAP - 64
 constexpr int BH_BYTES = (BN / 2) * BK * 2;  // this CTA's half of a B tile (128 item rows x 64 k)
 constexpr int MAX_STAGES = 8;
+constexpr int SN = 128;                      // accumulator stage width: a 256-column tile is two N = 128 MMAs
+constexpr int NACC = 4;                      // accumulator stages (4 x 128 = all 512 TMEM columns)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -60,6 +62,14 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
+}
+// one lane of a converged warp (the role loops stay warp-uniform, so tile counters, shared-memory addresses and
+// descriptors live in uniform registers and feed UTMALDG / UTCHMMA without a per-instruction R2UR + BRA.U.ANY loop:
+// with a single-thread issuer the loop was ~160 dependent SASS instructions per tile and paced the whole kernel)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
 }
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -123,7 +133,7 @@ __device__ __forceinline__ void tmem_wait_ld(float (&a)[32], float (&b)[32]) {
 }
 
 // kind::f16 instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
-constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // All 32 lanes call this for the same list.  Keeps the k best of `cnt` (> k) entries, returns the k-th value.
 __device__ __noinline__ float warp_prune(float *bv, int *bi, int cnt, int k, int lane) {
@@ -246,7 +256,8 @@ __device__ __forceinline__ void apply_history(HistCursor &hc, float (&r0)[32], f
 }
 
 // rare path: append every score above the threshold (8-column groups without one are skipped)
-__device__ __forceinline__ void collect(const float (&r)[32], int col0, float thr, float *lv, int *li, int &cnt) {
+// (`li_off`: distance in words from the value lists to the column lists -- one live pointer instead of two)
+__device__ __forceinline__ void collect(const float (&r)[32], int col0, float thr, float *lv, long long li_off, int &cnt) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (max8(r, g) > thr) {
@@ -254,12 +265,59 @@ __device__ __forceinline__ void collect(const float (&r)[32], int col0, float th
             for (int j = 8 * g; j < 8 * g + 8; ++j) {
                 if (r[j] > thr) {
                     __stcg(lv + cnt, r[j]);
-                    __stcg(li + cnt, col0 + j);
+                    __stcg(reinterpret_cast<int *>(lv) + li_off + cnt, col0 + j);
                     ++cnt;
                 }
             }
         }
     }
+}
+
+// mbarrier wait on a precomputed shared-memory address: the fast path is one try_wait + branch; the bounded spin
+// (rank_common.cuh: a protocol bug must trap, not hang) stays out of line
+__device__ __forceinline__ bool mbar_try_a(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_spin_a(uint32_t addr, uint32_t parity) {
+    long long t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try_a(addr, parity)) return;
+        if ((spins & 255u) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) {
+                printf("foodrec_b200 rank_topk_pair: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+    if (!mbar_try_a(addr, parity)) mbar_spin_a(addr, parity);
+}
+
+// One visit of a tile by an epilogue warp: wait for the MMAs of its accumulator stage, load both 32-column halves of its
+// quarter with one wait, and hand the stage back to the MMA issuer at once (the scores are in registers).  Tiles are
+// visited in (even, odd) pairs so the stage, its barriers and its TMEM address are compile-time offsets of
+// `tf` (shared address of tfull[q & 1]), `te` (cluster address of the leader's tempty[q & 1]) and `tl`.
+template <int ODD>
+__device__ __forceinline__ void visit_tile(uint32_t tf, uint32_t te, uint32_t tl, uint32_t ph, float (&r0)[32], float (&r1)[32]) {
+    mbar_wait_a(tf + 16 * ODD, ph);
+    tc_fence_after();
+    tmem_ld32_async(tl + 2 * SN * ODD, r0);
+    tmem_ld32_async(tl + 2 * SN * ODD + 32, r1);
+    tmem_wait_ld(r0, r1);
+    tc_fence_before();
+    __syncwarp();
+    if (elect_one()) mbar_arrive_cluster(te + 16 * ODD);
 }
 
 template <bool AFFINE, bool ARES>   // AFFINE: scores are scale * acc + bias[col];  ARES: the A block stays resident (K <= 128)
@@ -276,8 +334,8 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint32_t *thr_key = reinterpret_cast<uint32_t *>(smem + PP.off_thr);     // [BM] best known k-th key per row
     uint32_t *gkey = reinterpret_cast<uint32_t *>(smem + PP.off_gkey);       // [NG][BM] group maxima (pass 0)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PP.off_bars);
-    uint64_t *full = bars, *empty = bars + MAX_STAGES, *tfull = bars + 2 * MAX_STAGES, *tempty = tfull + ACC_STAGES;
-    uint64_t *afull = tempty + ACC_STAGES, *aempty = afull + 2;
+    uint64_t *full = bars, *empty = bars + MAX_STAGES, *tfull = bars + 2 * MAX_STAGES, *tempty = tfull + NACC;
+    uint64_t *afull = tempty + NACC, *aempty = afull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -290,7 +348,7 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 2 * EW); }
+        for (int s = 0; s < NACC; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, EW); }   // 8 warps x 2 CTAs per stage
         for (int s = 0; s < 2; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -309,7 +367,8 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     if (warp == 0) {
         // ================================ TMA producer (both CTAs) ================================
-        if (lane == 0) {
+        {
+            const bool elected = elect_one();
             int stage = 0, ab = 0;
             uint32_t phase = 0, abphase = 0;
             const uint32_t full0 = mapa(smem_u32(full), 0), afull0 = mapa(smem_u32(afull), 0);   // the leader's barriers
@@ -317,54 +376,107 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const int row0 = sb * 2 * BM + (int)rank * BM;
                 if (ARES) {
                     mbar_wait(aempty + ab, abphase ^ 1);
-                    if (leader) mbar_expect_tx(afull + ab, 2u * (uint32_t)n_kblk * A_BYTES);
-                    for (int kb = 0; kb < n_kblk; ++kb)
-                        tma_load_2d_pair(&tmA, afull0 + 8u * ab, ares + (size_t)(ab * n_kblk + kb) * A_BYTES, kb * BK, row0);
+                    if (elected) {
+                        if (leader) mbar_expect_tx(afull + ab, 2u * (uint32_t)n_kblk * A_BYTES);
+                        for (int kb = 0; kb < n_kblk; ++kb)
+                            tma_load_2d_pair(&tmA, afull0 + 8u * ab, ares + (size_t)(ab * n_kblk + kb) * A_BYTES, kb * BK, row0);
+                    }
+                    __syncwarp();
                     if (++ab == 2) { ab = 0; abphase ^= 1; }
                 }
-                for (int pass = 0; pass < n_pass; ++pass)
-                    for (int nb = 0; nb < n_nblk; nb += (n_pass == 2 && pass == 0) ? bstride : 1)
+                for (int pass = 0; pass < n_pass; ++pass) {
+                    // every sweep visits an EVEN number of tiles (an odd sweep gets one dummy visit past the last tile,
+                    // which the epilogue reads as all -inf), so a sweep always starts on accumulator stages 0 / 1
+                    const int step = (n_pass == 2 && pass == 0) ? bstride : 1;
+                    const int n_vis = (n_nblk + step - 1) / step, n_vis2 = n_vis + (n_vis & 1);
+                    for (int v = 0; v < n_vis2; ++v) {
+                        const int nb = min(v * step, n_nblk - 1);
                         for (int kb = 0; kb < n_kblk; ++kb) {
                             mbar_wait(empty + stage, phase ^ 1);
-                            uint8_t *st = ring + (size_t)stage * STG_BYTES;
-                            if (leader) mbar_expect_tx(full + stage, 2u * STG_BYTES);
-                            if (!ARES) tma_load_2d_pair(&tmA, full0 + 8u * stage, st, kb * BK, row0);
-                            tma_load_2d_pair(&tmB, full0 + 8u * stage, st + STG_A, kb * BK, nb * BN + (int)rank * (BN / 2));
+                            if (elected) {
+                                uint8_t *st = ring + (size_t)stage * STG_BYTES;
+                                if (leader) mbar_expect_tx(full + stage, 2u * STG_BYTES);
+                                if (!ARES) tma_load_2d_pair(&tmA, full0 + 8u * stage, st, kb * BK, row0);
+                                tma_load_2d_pair(&tmB, full0 + 8u * stage, st + STG_A, kb * BK, nb * BN + (int)rank * (BN / 2));
+                            }
+                            __syncwarp();
                             if (++stage == S) { stage = 0; phase ^= 1; }
                         }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (one lane of the leader CTA) ==================
-        if (leader && lane == 0) {
-            int stage = 0, as = 0, ab = 0;
-            uint32_t phase = 0, aphase = 0, abphase = 0;
+        // A 256-column tile is issued as two N = 128 MMAs per K step (B rows 0-63 / 64-127 of each CTA's half tile)
+        // into two of the FOUR accumulator stages, so the epilogue warps that own one half start a quarter of a tile
+        // time before the others and a stage is back 128 columns at a time.  Stage s of tile t: 2 (t & 1) + s.
+        if (leader) {
+            const bool elected = elect_one();
+            int stage = 0, ab = 0;
+            uint32_t phase = 0, abphase = 0, ti = 0;
             for (int sb = pair; sb < n_sblk; sb += n_pairs) {
                 if (ARES) {
                     mbar_wait(afull + ab, abphase);
                     tc_fence_after();
                 }
-                for (int pass = 0; pass < n_pass; ++pass)
-                    for (int nb = 0; nb < n_nblk; nb += (n_pass == 2 && pass == 0) ? bstride : 1) {
-                        mbar_wait(tempty + as, aphase ^ 1);      // both CTAs' epilogues have drained this accumulator
-                        tc_fence_after();
-                        for (int kb = 0; kb < n_kblk; ++kb) {
+                for (int pass = 0; pass < n_pass; ++pass) {
+                    const int step = (n_pass == 2 && pass == 0) ? bstride : 1;
+                    const int n_vis = (n_nblk + step - 1) / step, n_vis2 = n_vis + (n_vis & 1);
+                    for (int v = 0; v < n_vis2; ++v, ++ti) {
+                        const int s0 = 2 * (int)(ti & 1u);
+                        const uint32_t tph = (ti >> 1) & 1u;
+                        if (n_kblk == 1) {
                             mbar_wait(full + stage, phase);
-                            tc_fence_after();
                             const uint32_t st = smem_u32(ring + (size_t)stage * STG_BYTES);
-                            const uint32_t a = ARES ? smem_u32(ares + (size_t)(ab * n_kblk + kb) * A_BYTES) : st;
+                            const uint32_t a = ARES ? smem_u32(ares + (size_t)(ab * n_kblk) * A_BYTES) : st;
                             const uint64_t ad = make_desc(a), bd = make_desc(st + STG_A);
 #pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; ++k)    // +32 B per K step inside the swizzle atom
-                                umma_f16_pair(tmem_base + as * BN, ad + 2 * k, bd + 2 * k, kIdescPair, (kb | k) != 0);
-                            umma_commit_pair(empty + stage);                       // frees the slot in both CTAs
-                            if (kb == n_kblk - 1) umma_commit_pair(tfull + as);    // accumulator complete in both CTAs
+                            for (int s = 0; s < 2; ++s) {
+                                mbar_wait(tempty + s0 + s, tph ^ 1);     // both CTAs' epilogues have drained this stage
+                                tc_fence_after();
+                                if (elected) {
+#pragma unroll
+                                    for (int k = 0; k < BK / UMMA_K; ++k)    // +32 B per K step inside the swizzle atom
+                                        umma_f16_pair(tmem_base + (s0 + s) * SN, ad + 2 * k, bd + s * (BH_BYTES / 32) + 2 * k, kIdescPair, k != 0);
+                                    umma_commit_pair(tfull + s0 + s);         // this half of the tile is complete in both CTAs
+                                    if (s == 1) umma_commit_pair(empty + stage);   // frees the slot in both CTAs
+                                }
+                                __syncwarp();
+                            }
                             if (++stage == S) { stage = 0; phase ^= 1; }
+                        } else {
+                            mbar_wait(tempty + s0, tph ^ 1);
+                            mbar_wait(tempty + s0 + 1, tph ^ 1);
+                            tc_fence_after();
+                            for (int kb = 0; kb < n_kblk; ++kb) {
+                                mbar_wait(full + stage, phase);
+                                tc_fence_after();
+                                const uint32_t st = smem_u32(ring + (size_t)stage * STG_BYTES);
+                                const uint32_t a = ARES ? smem_u32(ares + (size_t)(ab * n_kblk + kb) * A_BYTES) : st;
+                                const uint64_t ad = make_desc(a), bd = make_desc(st + STG_A);
+                                if (elected) {
+#pragma unroll
+                                    for (int s = 0; s < 2; ++s)
+#pragma unroll
+                                        for (int k = 0; k < BK / UMMA_K; ++k)
+                                            umma_f16_pair(tmem_base + (s0 + s) * SN, ad + 2 * k, bd + s * (BH_BYTES / 32) + 2 * k, kIdescPair,
+                                                          (kb | k) != 0);
+                                    umma_commit_pair(empty + stage);
+                                    if (kb == n_kblk - 1) {
+                                        umma_commit_pair(tfull + s0);
+                                        umma_commit_pair(tfull + s0 + 1);
+                                    }
+                                }
+                                __syncwarp();
+                                if (++stage == S) { stage = 0; phase ^= 1; }
+                            }
                         }
-                        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
                     }
+                }
                 if (ARES) {
-                    umma_commit_pair(aempty + ab);          // the A block may be overwritten once these MMAs retire
+                    if (elected) umma_commit_pair(aempty + ab);          // the A block may be overwritten once these MMAs retire
+                    __syncwarp();
                     if (++ab == 2) { ab = 0; abphase ^= 1; }
                 }
             }
@@ -376,32 +488,15 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int q = ew >> 2;                   // column quarter of every tile handled by this warp
         const int r_in_blk = lg * 32 + lane;
         const int kk = P.topk;
-        const size_t list0 = (((size_t)blockIdx.x * BM + lg * 32) * 4 + q) * CAP;   // lane 0's list of this warp
-        float *lv = PP.lv + list0 + (size_t)lane * 4 * CAP;
-        int *li = PP.li + list0 + (size_t)lane * 4 * CAP;
-        const uint32_t tempty0 = mapa(smem_u32(tempty), 0);      // the MMA issuer waits on the leader's barriers
-        const uint32_t tlane = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)q * 64;
-        int as = 0;
-        uint32_t aphase = 0;
-        // One visit of a tile: both halves of the quarter are loaded with one wait, the accumulator stage is handed back
-        // to the MMA issuer at once (the scores are in registers), then tails / affine map / history are applied.
-        auto load_tile = [&](float (&r0)[32], float (&r1)[32], int col0, HistCursor &hc) {
-            mbar_wait(tfull + as, aphase);
-            tc_fence_after();
-            tmem_ld32_async(tlane + as * BN, r0);
-            tmem_ld32_async(tlane + as * BN + 32, r1);
-            tmem_wait_ld(r0, r1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty0 + 8u * as);
-            if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
-            const int valid = P.N - col0;
-            if (AFFINE || valid < 64) {
-                fix_scores<AFFINE>(r0, P, col0, min(32, valid));
-                fix_scores<AFFINE>(r1, P, col0 + 32, min(32, valid - 32));
-            }
-            if (hc.h0 < col0 + 64) apply_history(hc, r0, r1, col0);
-        };
+        float *const lv = PP.lv + ((((size_t)blockIdx.x * BM + r_in_blk) * 4 + q) * CAP);   // this thread's candidate list
+        const long long li_off = reinterpret_cast<const int *>(PP.li) - reinterpret_cast<const int *>(PP.lv);
+        // quarter q = items [64 q, 64 q + 64) of a tile = columns 64 (q >> 1) .. of accumulator stage 2 (t & 1) + (q & 1);
+        // the MMA issuer waits on the LEADER's `tempty` barriers
+        const uint32_t tf = smem_u32(tfull + (q & 1));
+        const uint32_t te = mapa(smem_u32(tempty + (q & 1)), 0);
+        const uint32_t tl = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(q & 1) * SN + (uint32_t)(q >> 1) * 64;
+        const uint32_t thr_a = smem_u32(thr_key + r_in_blk);
+        uint32_t ph = 0;                         // phase of the stage barriers: flips after every (even, odd) pair of visits
         for (int sb = pair; sb < n_sblk; sb += n_pairs) {
             const int row_blk0 = sb * 2 * BM + (int)rank * BM;
             const int row = row_blk0 + r_in_blk;
@@ -414,6 +509,18 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 hc.base = P.hist_idx + hlo;
                 hc.n = (int)(P.hist_ptr[id + 1] - hlo);
             }
+            // tails / affine map / history of one visited quarter (`checked`: the last pair of a sweep, which may hold
+            // the ragged tile and the dummy visit)
+            auto fix = [&](float (&r0)[32], float (&r1)[32], int col0, bool checked) {
+                if (AFFINE || checked) {
+                    const int valid = P.N - col0;
+                    if (AFFINE || valid < 64) {
+                        fix_scores<AFFINE>(r0, P, col0, min(32, valid));
+                        fix_scores<AFFINE>(r1, P, col0 + 32, min(32, valid - 32));
+                    }
+                }
+                if (hc.h0 < col0 + 64) apply_history(hc, r0, r1, col0);
+            };
             if (n_pass == 2) {
                 // ---------------- pass 0: group maxima -> lower bound of the k-th eligible score (masked columns are
                 // poisoned before the maxima, so the k-th largest group maximum bounds the k-th ELIGIBLE score)
@@ -421,13 +528,13 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 // num = (4 i + q) NG - gid * den stays in [0, den)
                 hc.reset();
                 float gmax = -INFINITY;
-                const long long den = 4LL * ((n_nblk + bstride - 1) / bstride);
+                const int n_vis = (n_nblk + bstride - 1) / bstride;
+                const long long den = 4LL * n_vis;
                 int gid = (int)(((long long)q * NG) / den);
                 long long num = (long long)q * NG - (long long)gid * den;
                 int gcur = gid;
-                for (int nb = 0; nb < n_nblk; nb += bstride) {
-                    float r0[32], r1[32];
-                    load_tile(r0, r1, nb * BN + q * 64, hc);
+                auto bound_tile = [&](float (&r0)[32], float (&r1)[32], int col0, bool checked) {
+                    fix(r0, r1, col0, checked);
                     if (gid != gcur) {
                         if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
                         gmax = -INFINITY;
@@ -436,8 +543,17 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     gmax = max3(gmax, max32(r0), max32(r1));
                     num += 4LL * NG;                      // next visited tile: (4 (i + 1) + q) NG
                     while (num >= den) { num -= den; ++gid; }
+                };
+                for (int v = 0; v < n_vis; v += 2) {
+                    const bool checked = v + 2 >= n_vis;
+                    float r0[32], r1[32];
+                    visit_tile<0>(tf, te, tl, ph, r0, r1);
+                    bound_tile(r0, r1, v * bstride * BN + q * 64, checked);
+                    visit_tile<1>(tf, te, tl, ph, r0, r1);
+                    bound_tile(r0, r1, (v + 1) * bstride * BN + q * 64, checked);
+                    ph ^= 1u;
                 }
-                if (gmax > -INFINITY) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
+                if (gmax > -INFINITY && gcur < NG) atomicMax(gkey + gcur * BM + r_in_blk, order_key(gmax));
                 __threadfence_block();
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + lg), "r"(128) : "memory");
                 // warp q of the lane group bounds rows q*8 .. q*8+7: the k-th largest of NG group maxima
@@ -466,34 +582,45 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             // -------------------- collection sweep
             hc.reset();
-            for (int nb = 0; nb < n_nblk; ++nb) {
-                float r0[32], r1[32];
-                const int col0 = nb * BN + q * 64;
-                load_tile(r0, r1, col0, hc);
-                const uint32_t shared_key = thr_key[r_in_blk];
-                if (shared_key != 0u) thr = fmaxf(thr, key_value(shared_key));
-                // hot path: 3-input max trees, one compare per 64 scores
-                if (fmaxf(max32(r0), max32(r1)) > thr) {
-                    // only the lanes (rows) that hold a candidate come here, and each walks only the 8-column groups
-                    // that hold one: the cost follows the number of candidates (-inf never passes)
-                    collect(r0, col0, thr, lv, li, cnt);
-                    collect(r1, col0 + 32, thr, lv, li, cnt);
-                }
-                // lists that could overflow on the next visit are pruned by the whole warp
-                uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 64);
-                if (need) { __threadfence_block(); __syncwarp(); }
-                while (need) {
-                    const int src = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int c_src = __shfl_sync(0xffffffffu, cnt, src);
-                    const float t_new = warp_prune(PP.lv + list0 + (size_t)src * 4 * CAP, PP.li + list0 + (size_t)src * 4 * CAP,
-                                                   c_src, kk, lane);
-                    if (lane == src) {
-                        thr = fmaxf(thr, t_new);
-                        cnt = kk;
-                        atomicMax(thr_key + r_in_blk, order_key(t_new));   // a bound every quarter of the row may use
+            // hot path per tile: two 3-input max trees, one compare, one vote.  A warp leaves it only when one of its
+            // rows holds a candidate; then just those lanes walk the 8-column groups that hold one (-inf never passes)
+            auto collect_tile = [&](float (&r0)[32], float (&r1)[32], int col0, bool checked) {
+                fix(r0, r1, col0, checked);
+                const float m0 = max32(r0), m1 = max32(r1);
+                if (__any_sync(0xffffffffu, fmaxf(m0, m1) > thr)) {
+                    if (m0 > thr) collect(r0, col0, thr, lv, li_off, cnt);
+                    if (m1 > thr) collect(r1, col0 + 32, thr, lv, li_off, cnt);
+                    // lists that could overflow on the next visit are pruned by the whole warp
+                    uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 64);
+                    if (need) {
+                        __threadfence_block();
+                        __syncwarp();
+                        float *const l0 = PP.lv + ((((size_t)blockIdx.x * BM + lg * 32) * 4 + q) * CAP);   // lane 0's list
+                        do {
+                            const int src = __ffs(need) - 1;
+                            need &= need - 1;
+                            const int c_src = __shfl_sync(0xffffffffu, cnt, src);
+                            const float t_new = warp_prune(l0 + (size_t)src * 4 * CAP, reinterpret_cast<int *>(l0) + li_off + (size_t)src * 4 * CAP,
+                                                           c_src, kk, lane);
+                            if (lane == src) {
+                                thr = fmaxf(thr, t_new);
+                                cnt = kk;
+                                atomicMax(thr_key + r_in_blk, order_key(t_new));   // a bound every quarter of the row may use
+                            }
+                        } while (need);
                     }
                 }
+            };
+            const int col_last = ((n_nblk - 1) & ~1) * BN + q * 64;      // first tile of the last (checked) pair
+            for (int col0 = q * 64; col0 <= col_last; col0 += 2 * BN) {
+                const uint32_t shared_key = lds32(thr_a);
+                if (shared_key != 0u) thr = fmaxf(thr, key_value(shared_key));
+                float r0[32], r1[32];
+                visit_tile<0>(tf, te, tl, ph, r0, r1);
+                collect_tile(r0, r1, col0, col0 == col_last);
+                visit_tile<1>(tf, te, tl, ph, r0, r1);
+                collect_tile(r0, r1, col0 + BN, col0 == col_last);
+                ph ^= 1u;
             }
             // ---- end of the row block: trim own lists to k, publish counts, merge the four quarters per row
             {
@@ -503,7 +630,8 @@ rank_topk_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const int c_src = __shfl_sync(0xffffffffu, cnt, src);
-                    warp_prune(PP.lv + list0 + (size_t)src * 4 * CAP, PP.li + list0 + (size_t)src * 4 * CAP, c_src, kk, lane);
+                    const size_t l_src = (((size_t)blockIdx.x * BM + lg * 32 + src) * 4 + q) * CAP;
+                    warp_prune(PP.lv + l_src, PP.li + l_src, c_src, kk, lane);
                     if (lane == src) cnt = kk;
                 }
             }

@@ -922,8 +922,8 @@ def _bench_knn(ds, dev, tpeak):
         ms = timed_ms(lambda: E.gemm_topk(xn, xn, k, A_bf16=xb, B_bf16=xb, b_max_norm=bmax, stats=st), 3, warm=1)
         E.PROFILE = None
         torch.cuda.synchronize()
-        kms = min(p[0].elapsed_time(p[1]) for p in prof)
         fl = 2.0 * x.shape[0] * x.shape[0] * x.shape[1]
+        kms = min(p[0].elapsed_time(p[1]) for p in prof if p[2] >= 0.99 * fl)    # full launches only, not the re-runs of uncertified rows
         out[name] = {"workload": f"{x.shape[0]} x {x.shape[0]} cosine similarities, D = {x.shape[1]}, top-{k} (self kept)",
                      "ms_total": ms, "kernel_ms": kms, "exactness": dict(st),
                      "roofline": {"bound": "tensor", "achieved": fl / (kms * 1e-3) / 1e12, "peak": tpeak[0], "unit": "TFLOP/s",

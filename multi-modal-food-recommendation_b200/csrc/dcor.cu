@@ -47,6 +47,18 @@ __device__ __forceinline__ float block_sum(float v, float *sh) {
     return t;
 }
 
+__device__ __forceinline__ double block_sum_d(double v, double *sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < kThreads / 32; ++i) t += sh[i];
+    return t;
+}
+
 // ---------------------------------------------------------------------------------------- K1
 // 64 x 64 tile of D_v per CTA (256 threads, 4 x 4 outputs each) from transposed shared tiles of the
 // gathered rows; squared norms ride along in the k loop in the same summation order as the dot product,
@@ -114,58 +126,65 @@ dcor_dist_kernel(Views vw, const int64_t *__restrict__ idx, int n, float *__rest
     }
 }
 
+// The centring and the six inner products run in DOUBLE (B200's fp64 pipe makes that free at n = 1024): the cross
+// products sum_ij A_v A_w of nearly independent views cancel to ~1e-3 of their absolute mass, and with fp32 centring
+// their rounding error reached the gradients through 1 / (2 sqrt(s_vw)) at ~3e-5 relative (the reference's own fp32
+// autograd sits at 3e-4..7e-4 from the fp64 result; with double centring this path is at ~7e-7).
 __global__ void dcor_rowmean_kernel(const float *__restrict__ rowpart, int n, int n_tiles, int V,
-                                    float *__restrict__ rowmean) {
+                                    float *__restrict__ rowmean, double *__restrict__ rowmean64) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
     if (i >= n) return;
-    float s = 0.f;
-    for (int t = 0; t < n_tiles; ++t) s += rowpart[((size_t)v * n_tiles + t) * n + i];
-    rowmean[(size_t)v * n + i] = s / (float)n;
+    double s = 0.0;
+    for (int t = 0; t < n_tiles; ++t) s += (double)rowpart[((size_t)v * n_tiles + t) * n + i];
+    s /= (double)n;
+    rowmean64[(size_t)v * n + i] = s;
+    rowmean[(size_t)v * n + i] = (float)s;
 }
 
 // ---------------------------------------------------------------------------------------- K2
 // out layout: out[p] = dcor_p; dfds[p*3 + {0,1,2}] = d dcor_p / d {s_ab, s_aa, s_bb}; gm[v] grand means.
 __global__ void __launch_bounds__(kThreads)
-dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const float *__restrict__ rowmean,
+dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const double *__restrict__ rowmean,
                 float *__restrict__ out, float *__restrict__ dfds, float *__restrict__ gm_out,
                 float *__restrict__ ws, float scale) {
-    __shared__ float red[kThreads / 32];
-    __shared__ float gm[kMaxV];
-    __shared__ float fin[6];
+    __shared__ double red[kThreads / 32];
+    __shared__ double gm[kMaxV];
+    __shared__ double fin[6];
     __shared__ int last;
+    double *__restrict__ part = reinterpret_cast<double *>(ws + 8);     // [grid][8] block partials
     for (int v = 0; v < V; ++v) {
-        float s = 0.f;
-        for (int j = threadIdx.x; j < n; j += kThreads) s += __ldg(rowmean + (size_t)v * n + j);
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) gm[v] = s / (float)n;
+        double s = 0.0;
+        for (int j = threadIdx.x; j < n; j += kThreads) s += rowmean[(size_t)v * n + j];
+        s = block_sum_d(s, red);
+        if (threadIdx.x == 0) gm[v] = s / (double)n;
     }
     __syncthreads();
     // accumulate s[v][w], v <= w, slot = v*3 + w - (v*(v+1))/2 -> (00,01,02,11,12,22)
-    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int i0 = blockIdx.x * kRB2;
     for (int r = 0; r < kRB2 && i0 + r < n; ++r) {
         const int i = i0 + r;
-        float rmi[kMaxV];
-        for (int v = 0; v < kMaxV; ++v) rmi[v] = v < V ? __ldg(rowmean + (size_t)v * n + i) : 0.f;
+        double rmi[kMaxV];
+        for (int v = 0; v < kMaxV; ++v) rmi[v] = v < V ? rowmean[(size_t)v * n + i] : 0.0;
 #pragma unroll 4
         for (int j = threadIdx.x; j < n; j += kThreads) {
-            float A[kMaxV];
+            double A[kMaxV];
 #pragma unroll
             for (int v = 0; v < kMaxV; ++v)
-                A[v] = v < V ? (((__ldg(Dm + ((size_t)v * n + i) * n + j) - __ldg(rowmean + (size_t)v * n + j)) - rmi[v]) + gm[v])
-                             : 0.f;
-            acc[0] = fmaf(A[0], A[0], acc[0]);
-            acc[1] = fmaf(A[0], A[1], acc[1]);
-            acc[2] = fmaf(A[0], A[2], acc[2]);
-            acc[3] = fmaf(A[1], A[1], acc[3]);
-            acc[4] = fmaf(A[1], A[2], acc[4]);
-            acc[5] = fmaf(A[2], A[2], acc[5]);
+                A[v] = v < V ? ((((double)__ldg(Dm + ((size_t)v * n + i) * n + j) - rowmean[(size_t)v * n + j]) - rmi[v]) + gm[v])
+                             : 0.0;
+            acc[0] = fma(A[0], A[0], acc[0]);
+            acc[1] = fma(A[0], A[1], acc[1]);
+            acc[2] = fma(A[0], A[2], acc[2]);
+            acc[3] = fma(A[1], A[1], acc[3]);
+            acc[4] = fma(A[1], A[2], acc[4]);
+            acc[5] = fma(A[2], A[2], acc[5]);
         }
     }
     for (int q = 0; q < 6; ++q) {
-        const float s = block_sum(acc[q], red);
-        if (threadIdx.x == 0) __stcg(ws + 8 + (size_t)blockIdx.x * 8 + q, s);
+        const double s = block_sum_d(acc[q], red);
+        if (threadIdx.x == 0) __stcg(part + (size_t)blockIdx.x * 8 + q, s);
     }
     __threadfence();
     __syncthreads();
@@ -174,33 +193,34 @@ dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const floa
     if (!last) return;
     __threadfence();
     if (threadIdx.x < 6) {
-        float s = 0.f;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(ws + 8 + (size_t)b * 8 + threadIdx.x);
-        fin[threadIdx.x] = s / ((float)n * (float)n);
+        double s = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(part + (size_t)b * 8 + threadIdx.x);
+        fin[threadIdx.x] = s / ((double)n * (double)n);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        auto S = [&](int a, int b) -> float {
+        auto S = [&](int a, int b) -> double {
             if (a > b) { const int t = a; a = b; b = t; }
             return fin[a * 3 + b - (a * (a + 1)) / 2];
         };
-        float total = 0.f;
+        double total = 0.0;
         for (int p = 0; p < pr.P; ++p) {
             const int a = pr.a[p], b = pr.b[p];
-            const float sab = S(a, b), saa = S(a, a), sbb = S(b, b);
-            const float cab = sqrtf(fmaxf(sab, 0.f) + 1e-8f);
-            const float caa = sqrtf(fmaxf(saa, 0.f) + 1e-8f);
-            const float cbb = sqrtf(fmaxf(sbb, 0.f) + 1e-8f);
-            const float q = sqrtf(fmaxf(caa * cbb, 0.f) + 1e-10f);
-            out[p] = scale * (cab / q);
-            total += out[p];
-            const float dq = -cab / (2.f * q * q * q);  // d f / d (caa*cbb)
-            dfds[p * 3 + 0] = sab > 0.f ? scale / (2.f * cab * q) : 0.f;
-            dfds[p * 3 + 1] = saa > 0.f ? scale * dq * cbb / (2.f * caa) : 0.f;
-            dfds[p * 3 + 2] = sbb > 0.f ? scale * dq * caa / (2.f * cbb) : 0.f;
+            const double sab = S(a, b), saa = S(a, a), sbb = S(b, b);
+            const double cab = sqrt(fmax(sab, 0.0) + 1e-8);
+            const double caa = sqrt(fmax(saa, 0.0) + 1e-8);
+            const double cbb = sqrt(fmax(sbb, 0.0) + 1e-8);
+            const double q = sqrt(fmax(caa * cbb, 0.0) + 1e-10);
+            const double o = (double)scale * (cab / q);
+            out[p] = (float)o;
+            total += o;
+            const double dq = -cab / (2.0 * q * q * q);  // d f / d (caa*cbb)
+            dfds[p * 3 + 0] = sab > 0.0 ? (float)((double)scale / (2.0 * cab * q)) : 0.f;
+            dfds[p * 3 + 1] = saa > 0.0 ? (float)((double)scale * dq * cbb / (2.0 * caa)) : 0.f;
+            dfds[p * 3 + 2] = sbb > 0.0 ? (float)((double)scale * dq * caa / (2.0 * cbb)) : 0.f;
         }
-        out[pr.P] = total;      // sum of the (scaled) terms, the value CLUSSL's loss uses
-        for (int v = 0; v < V; ++v) gm_out[v] = gm[v];
+        out[pr.P] = (float)total;      // sum of the (scaled) terms, the value CLUSSL's loss uses
+        for (int v = 0; v < V; ++v) gm_out[v] = (float)gm[v];
         *reinterpret_cast<int *>(ws) = 0;
     }
 }
@@ -329,10 +349,13 @@ int fill(Views &vw, Pairs &pr, int V, const float *const *tab, float *const *dta
 
 }  // namespace
 
-// ws layout: [0] ticket, [8 ...) dot-kernel block partials, then the row-sum partials [V][n_tiles][n]
+// ws layout (floats): [0] ticket, [8 ...) dot-kernel block partials (8 doubles per block), the double row means
+// [V][n], then the row-sum partials [V][n_tiles][n]
 static int64_t dot_blocks(int n) { return (n + kRB2 - 1) / kRB2; }
+static int64_t rm64_off(int n) { return 8 + 16 * dot_blocks(n); }
+static int64_t rowpart_off(int n) { return rm64_off(n) + 2 * (int64_t)kMaxV * n; }
 extern "C" int64_t fr_dcor_ws_floats(int32_t n) {
-    return 8 + 8 * dot_blocks(n) + (int64_t)kMaxV * ((n + kT - 1) / kT) * n;
+    return rowpart_off(n) + (int64_t)kMaxV * ((n + kT - 1) / kT) * n;
 }
 
 extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
@@ -344,7 +367,9 @@ extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, c
     if (int rc = fill(vw, pr, V, tab_host, nullptr, P, pairs_host)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = (n + kT - 1) / kT;
-    float *rowpart = ws + 8 + 8 * dot_blocks(n);
+    FR_REQUIRE(((uintptr_t)ws & 7) == 0, "fr_dcor_fwd: workspace must be 8-byte aligned");
+    float *rowpart = ws + rowpart_off(n);
+    double *rowmean64 = reinterpret_cast<double *>(ws + rm64_off(n));
     dim3 g1(n_tiles, n_tiles, V);
     {
     fr::LaunchTimer _lt("dcor_dist_kernel", st);
@@ -356,10 +381,10 @@ extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, c
     }
     }
     if (int rc = fr::check_launch("fr_dcor_fwd/dist")) return rc;
-    dcor_rowmean_kernel<<<dim3((n + 255) / 256, V), 256, 0, st>>>(rowpart, n, n_tiles, V, rowmean);
+    dcor_rowmean_kernel<<<dim3((n + 255) / 256, V), 256, 0, st>>>(rowpart, n, n_tiles, V, rowmean, rowmean64);
     if (int rc = fr::check_launch("fr_dcor_fwd/rowmean")) return rc;
     fr::LaunchTimer _lt2("dcor_dot_kernel", st);
-    dcor_dot_kernel<<<(n + kRB2 - 1) / kRB2, kThreads, 0, st>>>(V, pr, n, Dm, rowmean, out, dfds, gm, ws, scale);
+    dcor_dot_kernel<<<(n + kRB2 - 1) / kRB2, kThreads, 0, st>>>(V, pr, n, Dm, rowmean64, out, dfds, gm, ws, scale);
     return fr::check_launch("fr_dcor_fwd/dot");
 }
 

@@ -702,7 +702,7 @@ def _bench_eval_c4(dev, rank, world, barrier, tpeak):
     stats = {}
     gathered = torch.empty((per * world, k), dtype=torch.int32, device=dev) if world > 1 else None
     padded = torch.full((per, k), -1, dtype=torch.int32, device=dev) if world > 1 else None
-    block = 148 * 128 * 8        # users per launch: bounds the candidate buffers; 8 full waves of row blocks
+    block = M                    # one launch per rank: the kernel is persistent over 256-row blocks and its workspace is per CTA
 
     def run():
         outs = []

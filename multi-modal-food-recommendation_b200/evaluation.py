@@ -184,7 +184,9 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
     if n_bad:
         bad = torch.nonzero(cert == 0).reshape(-1)
         kc2 = min(MAX_K, N)
-        if kc2 > kc:       # second chance on the tensor cores: the widest candidate set for just these rows
+        # second chance on the tensor cores: the widest candidate set for just these rows -- unless they are too few to
+        # fill the tensor-core kernel (one 256-row block sweeps every column alone), where the exact fp32 kernel is faster
+        if kc2 > kc and n_bad > 1024:
             n_wide = n_bad
             A_bad = A[bad].contiguous()
             rid_bad = row_ids[bad].contiguous() if hist is not None else None

@@ -177,6 +177,32 @@ def ev_pair():
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
+def timed_graph_ms(fn, reps):
+    """Average device time of one `fn()` when `reps` of them run back to back: the calls are captured into a CUDA
+    graph (no Python between the launches) and one replay is timed with events."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(3):
+        a, b = ev_pair()
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best / reps
+
+
 def timed_ms(fn, iters, warm=2):
     """Median-free simple device timing: `iters` calls between one CUDA-event pair on the current stream."""
     for _ in range(warm):
@@ -369,18 +395,32 @@ def main():
     probe_tot, gathered = 0.0, 0.0          # the same launches' row gathers alone (`fr_probe_gather`): the gather roofline
     probe_out = torch.empty(148 * 32 * 32, device=dev)
     bufs = {}
-    for _, _, nb, g, has_z in prof:
-        key = (g.n_rows, g.n_cols)
+    def _buf(gr):
+        key = (gr.n_rows, gr.n_cols)
         if key not in bufs:
-            bufs[key] = (torch.randn(g.n_cols, 64, device=dev), torch.randn(g.n_rows, 64, device=dev),
-                         torch.empty(g.n_rows, 64, device=dev))
-        X, Z, Y = bufs[key]
-        tot_ms += timed_ms(lambda: ops.spmm(g, X, Z=Z if has_z else None, alpha=0.5, beta=0.5, out=Y), REP, warm=1)
+            bufs[key] = (torch.randn(gr.n_cols, 64, device=dev), torch.randn(gr.n_rows, 64, device=dev),
+                         torch.empty(gr.n_rows, 64, device=dev))
+        return bufs[key]
+
+    def _probe(gr, X):
+        _lib.check(_lib.lib.fr_probe_gather(X.data_ptr(), 64, gr.col.data_ptr(), gr.nnz, 8, 148 * 32, probe_out.data_ptr(),
+                                            _lib.stream_ptr()), "fr_probe_gather")
+    n_grouped = 0
+    for _, _, nb, g, has_z in prof:
+        if isinstance(g, ops.PropGroup):      # one grouped launch over several graphs (CLUSSL's item-side layer)
+            n_grouped += 1
+            bs = [_buf(gr) for gr in g.graphs]
+            Xs, Zs, Ys = [b[0] for b in bs], [b[1] if has_z else None for b in bs], [b[2] for b in bs]
+            tot_ms += timed_graph_ms(lambda: ops.spmm_grouped(g, Xs, Zs, 0.5, 0.5, outs=Ys), REP)
+            for gr, X in zip(g.graphs, Xs):
+                probe_tot += timed_ms(lambda: _probe(gr, X), REP, warm=1)
+                gathered += gr.nnz * 256.0
+        else:
+            X, Z, Y = _buf(g)
+            tot_ms += timed_graph_ms(lambda: ops.spmm(g, X, Z=Z if has_z else None, alpha=0.5, beta=0.5, out=Y), REP)
+            probe_tot += timed_ms(lambda: _probe(g, X), REP, warm=1)
+            gathered += g.nnz * 256.0
         tot_bytes += nb
-        probe_tot += timed_ms(lambda: _lib.check(_lib.lib.fr_probe_gather(
-            X.data_ptr(), 64, g.col.data_ptr(), g.nnz, 8, 148 * 32, probe_out.data_ptr(), _lib.stream_ptr()), "fr_probe_gather"),
-            REP, warm=1)
-        gathered += g.nnz * 256.0
     del bufs
     peaks = _peaks()
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
@@ -418,7 +458,8 @@ def main():
         "gpu_launches": int(launches) if step_mode == "eager" else int(launches_per_step_eager * timed_steps),
         "step_mode": step_mode,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "spmm_group_kernel<64,8,4>", "achieved": achieved, "peak": peaks[0],
+        "roofline": {"bound": "hbm", "kernel": "spmm_group_kernel<64,8,4> (user-item graph) + spmm_grouped_kernel<64> (the three "
+                                               "item-side graphs of a layer in one grid)", "achieved": achieved, "peak": peaks[0],
                      "unit": "GB/s", "frac": achieved / peaks[0], "traffic": _spmm_traffic(), "peak_source": peaks[1],
                      "traffic_source": "profiles/: mean dram read+write bytes per launch, ncu --set full over the propagation "
                                        "launches of one step (below the algorithmic bytes: the step's tables stay in the 126 MB L2)",

@@ -90,6 +90,32 @@ int fr_spmm_csr_f32_masked(const int32_t *seg, int64_t n_seg, const int32_t *lon
                            float alpha, float beta, float *Y, float *partial, int32_t *counters, const uint8_t *x_mask,
                            uint8_t *y_mask, void *stream);
 
+/* Grouped launch: up to FR_SPMM_MAX_TASKS independent propagations (own graph, own operands, fused `+ beta*Z`) in ONE
+ * grid.  CLUSSL's three item-side propagations of a layer (pricai_modelx.py:183,197,211: ingredient, image-cluster and
+ * text-cluster graphs) are each too small to fill the GPU; launched together their long-row tails overlap and a training
+ * step has 6 propagation launches instead of 14.  `blk_map` (device, int32 [n_blocks][2] = task, block of that task;
+ * fr_spmm_task_blocks(n_seg) blocks per task) fixes the order in which the tasks' blocks are scheduled.  Results are
+ * bit-identical to the separate fr_spmm_csr_f32_split calls. */
+#define FR_SPMM_MAX_TASKS 4
+typedef struct fr_spmm_task {
+    const int32_t *seg;
+    int64_t n_seg;
+    const int32_t *long_rows;
+    int64_t n_long;
+    const int32_t *col_idx;
+    const float *val;
+    const float *X0, *X1;
+    int32_t x_split;
+    const float *Z0, *Z1;
+    int32_t z_split;
+    float alpha, beta;
+    float *Y, *partial;
+    int32_t *counters;
+} fr_spmm_task;
+int64_t fr_spmm_task_blocks(int64_t n_seg);
+int fr_spmm_csr_f32_grouped(const fr_spmm_task *tasks_host, int32_t n_tasks, int32_t d, const int32_t *blk_map,
+                            int64_t n_blocks, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused ranking loss on gathered rows: BPR + embedding regulariser, forward and backward.
  * Replaces the gathers, `torch.mul(..).sum(1)`, `BPRLoss` and `EmbLoss` at

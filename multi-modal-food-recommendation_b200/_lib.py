@@ -40,6 +40,8 @@ SIGNATURES = {
     "fr_spmm_csr_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i32, _p, _p, _f32, _f32, _p, _i32, _p, _p, _p, _p]),
     "fr_spmm_csr_f32_split": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i32, _p, _p, _i32, _p, _p, _i32, _f32, _f32, _p, _i32,
                                         _p, _p, _p, _p]),
+    "fr_spmm_task_blocks": (_i64, [_i64]),
+    "fr_spmm_csr_f32_grouped": (C.c_int, [_p, _i32, _i32, _p, _i64, _p]),
     "fr_rank_loss_ws_floats": (_i64, []),
     "fr_rank_loss_fwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
     "fr_rank_loss_bwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _p]),
@@ -75,6 +77,13 @@ SIGNATURES = {
     "fr_schgn_attend": (C.c_int, [_p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "fr_schgn_score": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p]),
 }
+
+class SpmmTask(C.Structure):
+    """`fr_spmm_task` of include/foodrec_b200.h (one propagation of a grouped launch)."""
+    _fields_ = [("seg", _p), ("n_seg", _i64), ("long_rows", _p), ("n_long", _i64), ("col_idx", _p), ("val", _p),
+                ("X0", _p), ("X1", _p), ("x_split", _i32), ("Z0", _p), ("Z1", _p), ("z_split", _i32),
+                ("alpha", _f32), ("beta", _f32), ("Y", _p), ("partial", _p), ("counters", _p)]
+
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)

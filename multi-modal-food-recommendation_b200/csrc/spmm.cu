@@ -85,15 +85,16 @@ __device__ __forceinline__ bool epilogue_store(float4 acc, int row, int off, con
 // per-row bookkeeping of the warp-per-segment kernel (D = 64: 8 lanes x 2 float4, four rows per warp),
 // and the shuffle / address / predicate work of a step is shared by 4 nonzeros.  Groups of one warp take
 // adjacent segments of the length-sorted plan, so their trip counts match.
+// `w` = index of this warp among the warps of ONE propagation (the plain launch derives it from blockIdx; the grouped
+// launch, which runs several independent propagations in one grid, from its block map).
 template <int D, int LPR, int U, int ACT, bool SPLIT, bool MASKED, bool PUSH = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, FR_GROUP_MIN_BLOCKS)
-spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
-                  const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
-                  const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,
-                  float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters, Split sp) {
+__device__ __forceinline__ void
+spmm_group_body(const long long w, const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
+                const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
+                const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,
+                float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters, const Split &sp) {
     constexpr int G = 32 / LPR, VPL = D / (4 * LPR);
     static_assert(VPL >= 1 && LPR % U == 0, "bad group shape");
-    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w * G >= n_seg) return;
     const int lane = threadIdx.x & 31;
     const int g = lane / LPR, lg = lane % LPR;
@@ -194,6 +195,57 @@ spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__r
         if (lg == 0) sp.y_mask[lr.w] = nz_long ? 1 : 0;
     }
     if (lg == 0) counters[s.w] = 0;
+}
+
+template <int D, int LPR, int U, int ACT, bool SPLIT, bool MASKED, bool PUSH = false>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, FR_GROUP_MIN_BLOCKS)
+spmm_group_kernel(const int4 *__restrict__ seg, long long n_seg, const int4 *__restrict__ long_rows,
+                  const int *__restrict__ col, const float *__restrict__ val, const float *__restrict__ X,
+                  const float *__restrict__ Z, float alpha, float beta, const float *__restrict__ bias,
+                  float *__restrict__ Y, float *__restrict__ partial, int *__restrict__ counters, Split sp) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    spmm_group_body<D, LPR, U, ACT, SPLIT, MASKED, PUSH>(w, seg, n_seg, long_rows, col, val, X, Z, alpha, beta, bias, Y, partial,
+                                                         counters, sp);
+}
+
+// Grouped launch: up to FR_SPMM_MAX_TASKS independent propagations (different graphs, different operands) in ONE grid.
+// CLUSSL's three item-side graphs are each too small to fill 148 SMs and end in a tail of a few long rows; launched as
+// one grid their tails overlap and the step has 6 propagation launches instead of 14.  `blk_map[b] = (task, block of
+// that task)` interleaves the tasks' blocks in proportion, so every task's long-row segments (first in its plan) are
+// scheduled early.  Two-segment operands are always compiled in (x_split = INT_MAX: single table).
+struct GroupedTask {
+    const int4 *seg;
+    long long n_seg;
+    const int4 *long_rows;
+    const int *col;
+    const float *val;
+    const float *X, *X1_adj, *Z, *Z1_adj;
+    float *Y, *partial;
+    int *counters;
+    int x_split, z_split;
+    float alpha, beta;
+};
+struct GroupedParams {
+    GroupedTask t[FR_SPMM_MAX_TASKS];
+};
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, FR_GROUP_MIN_BLOCKS)
+spmm_grouped_kernel(const __grid_constant__ GroupedParams P, const int2 *__restrict__ blk_map) {
+    const int2 m = __ldg(blk_map + blockIdx.x);
+    const GroupedTask &T = P.t[m.x];
+    Split sp;
+    sp.X1_adj = T.X1_adj;
+    sp.x_split = T.x_split;
+    sp.Z1_adj = T.Z1_adj;
+    sp.z_split = T.z_split;
+    sp.x_mask = nullptr;
+    sp.y_mask = nullptr;
+    sp.n_peers = 0;
+    sp.row_off = 0;
+    const long long w = (long long)m.y * kWarpsPerBlock + (threadIdx.x >> 5);
+    spmm_group_body<D, 8, 4, 0, true, false, false>(w, T.seg, T.n_seg, T.long_rows, T.col, T.val, T.X, T.Z, T.alpha, T.beta,
+                                                    nullptr, T.Y, T.partial, T.counters, sp);
 }
 
 template <int D, int LPR, int U, int ACT>
@@ -402,4 +454,63 @@ extern "C" int fr_spmm_csr_f32(const int32_t *seg, int64_t n_seg, const int32_t 
                                int32_t *counters, void *stream) {
     return fr_spmm_csr_f32_split(seg, n_seg, long_rows, n_long, col_idx, val, d, X, nullptr, 0, Z, nullptr, 0, alpha, beta,
                                  bias, act, Y, partial, counters, stream);
+}
+
+extern "C" int64_t fr_spmm_task_blocks(int64_t n_seg) {
+    return (n_seg + 4 * kWarpsPerBlock - 1) / (4 * kWarpsPerBlock);     // 4 segments per warp, kWarpsPerBlock warps per block
+}
+
+extern "C" int fr_spmm_csr_f32_grouped(const fr_spmm_task *tasks_host, int32_t n_tasks, int32_t d, const int32_t *blk_map,
+                                       int64_t n_blocks, void *stream) {
+    FR_REQUIRE(tasks_host && n_tasks >= 1 && n_tasks <= FR_SPMM_MAX_TASKS, "fr_spmm_csr_f32_grouped: 1..%d tasks", FR_SPMM_MAX_TASKS);
+    FR_REQUIRE(blk_map && n_blocks >= 0 && n_blocks <= 0x7fffffffLL, "fr_spmm_csr_f32_grouped: bad block map");
+    if (n_blocks == 0) return FR_OK;
+    GroupedParams P;
+    int64_t blocks = 0;
+    for (int t = 0; t < FR_SPMM_MAX_TASKS; ++t) {
+        GroupedTask &T = P.t[t];
+        if (t >= n_tasks) {
+            T = P.t[0];
+            continue;
+        }
+        const fr_spmm_task &h = tasks_host[t];
+        FR_REQUIRE(h.n_seg >= 0 && h.n_long >= 0 && h.seg && h.X0 && h.Y, "fr_spmm_csr_f32_grouped: task %d: null pointer", t);
+        FR_REQUIRE(h.n_long == 0 || (h.long_rows && h.partial && h.counters), "fr_spmm_csr_f32_grouped: task %d: long rows need workspace", t);
+        FR_REQUIRE((((uintptr_t)h.X0 | (uintptr_t)h.X1 | (uintptr_t)h.Y | (uintptr_t)h.Z0 | (uintptr_t)h.Z1 | (uintptr_t)h.partial |
+                     (uintptr_t)h.seg | (uintptr_t)h.long_rows) & 15) == 0, "fr_spmm_csr_f32_grouped: task %d: pointers must be 16-byte aligned", t);
+        FR_REQUIRE(h.X0 != h.Y && h.X1 != h.Y, "fr_spmm_csr_f32_grouped: task %d: in-place propagation is not supported", t);
+        FR_REQUIRE(h.x_split >= 0 && h.z_split >= 0 && (h.X1 != nullptr || h.x_split == 0) && (h.Z1 == nullptr || h.Z0 != nullptr),
+                   "fr_spmm_csr_f32_grouped: task %d: bad split arguments", t);
+        T.seg = reinterpret_cast<const int4 *>(h.seg);
+        T.n_seg = h.n_seg;
+        T.long_rows = reinterpret_cast<const int4 *>(h.long_rows);
+        T.col = h.col_idx;
+        T.val = h.val;
+        T.X = h.X0;
+        T.x_split = h.X1 ? h.x_split : 0x7fffffff;
+        T.X1_adj = h.X1 ? h.X1 - (size_t)h.x_split * d : h.X0;
+        T.Z = h.Z0;
+        T.z_split = h.Z1 ? h.z_split : 0x7fffffff;
+        T.Z1_adj = h.Z1 ? h.Z1 - (size_t)h.z_split * d : h.Z0;
+        T.Y = h.Y;
+        T.partial = h.partial;
+        T.counters = h.counters;
+        T.alpha = h.alpha;
+        T.beta = h.beta;
+        blocks += fr_spmm_task_blocks(h.n_seg);
+    }
+    FR_REQUIRE(blocks == n_blocks, "fr_spmm_csr_f32_grouped: block map has %lld entries, the tasks need %lld", (long long)n_blocks,
+               (long long)blocks);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int2 *bm = reinterpret_cast<const int2 *>(blk_map);
+    fr::LaunchTimer _lt("spmm_grouped_kernel", st);
+    switch (d) {
+        case 32: spmm_grouped_kernel<32><<<(unsigned)n_blocks, kWarpsPerBlock * 32, 0, st>>>(P, bm); break;
+        case 64: spmm_grouped_kernel<64><<<(unsigned)n_blocks, kWarpsPerBlock * 32, 0, st>>>(P, bm); break;
+        case 128: spmm_grouped_kernel<128><<<(unsigned)n_blocks, kWarpsPerBlock * 32, 0, st>>>(P, bm); break;
+        default:
+            fr::set_error("fr_spmm_csr_f32_grouped: d=%d unsupported (32, 64, 128)", d);
+            return FR_EUNSUPPORTED;
+    }
+    return fr::check_launch("fr_spmm_csr_f32_grouped");
 }

@@ -94,23 +94,39 @@ class PRICAI_ModelX(DotProductRecommender):
             s1, s2 = self._side_streams()
         else:                       # serial execution (per-kernel timing in bench.py)
             s1 = s2 = cur
-        s1.wait_stream(cur)
-        s2.wait_stream(cur)
-        ing = ops.propagate_mean(self.g_ingre, item_w, self.n_ri_layers, bottom=self.ingre_embedding.weight[:-1])
-        with torch.cuda.stream(s1):
+        if getattr(self, "group_item_graphs", True):
+            # the three item-side propagations of a layer are ONE grouped launch (forward and backward): each graph
+            # alone is too small to fill the GPU and ends in a tail of long cluster / ingredient rows
             image_proto = self.image_prototype_embedding.weight
             if self.v_center is not None:
                 image_proto = self.image_trs(image_proto)
-            img = ops.propagate_mean(self.g_image, item_w, self.n_ri_layers, bottom=image_proto)
-        with torch.cuda.stream(s2):
             text_proto = self.text_prototype_embedding.weight
             if self.t_center is not None:
                 text_proto = self.text_trs(text_proto)
-            txt = ops.propagate_mean(self.g_text, item_w, self.n_ri_layers, bottom=text_proto)
-        cur.wait_stream(s1)
-        cur.wait_stream(s2)
-        for t in (img, txt):
-            t.record_stream(cur)
+            grp = getattr(self, "_item_group", None)
+            if grp is None:
+                grp = self._item_group = ops.PropGroup([self.g_ingre, self.g_image, self.g_text])
+            ing, img, txt = ops.propagate_mean_grouped(grp, [item_w, item_w, item_w],
+                                                       [self.ingre_embedding.weight[:-1], image_proto, text_proto],
+                                                       self.n_ri_layers)
+        else:
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+            ing = ops.propagate_mean(self.g_ingre, item_w, self.n_ri_layers, bottom=self.ingre_embedding.weight[:-1])
+            with torch.cuda.stream(s1):
+                image_proto = self.image_prototype_embedding.weight
+                if self.v_center is not None:
+                    image_proto = self.image_trs(image_proto)
+                img = ops.propagate_mean(self.g_image, item_w, self.n_ri_layers, bottom=image_proto)
+            with torch.cuda.stream(s2):
+                text_proto = self.text_prototype_embedding.weight
+                if self.t_center is not None:
+                    text_proto = self.text_trs(text_proto)
+                txt = ops.propagate_mean(self.g_text, item_w, self.n_ri_layers, bottom=text_proto)
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
+            for t in (img, txt):
+                t.record_stream(cur)
         side = None
         if side_fn is not None:   # training: item_emb and the contrastive total come from one fused op
             item_emb, side = side_fn(img, txt, ing)

@@ -200,6 +200,121 @@ def propagate_mean(graph: PropGraph, ego: torch.Tensor, n_layers: int, bottom: t
     return _PropagateMean2.apply(ego, bottom, graph, n_layers)
 
 
+# ----------------------------------------------------------------------------- grouped propagation
+class PropGroup:
+    """Several independent graphs propagated by ONE launch per layer (`fr_spmm_csr_f32_grouped`).  The block map
+    interleaves the graphs' blocks in proportion to their sizes, each graph in its own plan order (long-row segments
+    first), and is uploaded once."""
+
+    def __init__(self, graphs):
+        import numpy as np
+        self.graphs = list(graphs)
+        if not 1 <= len(self.graphs) <= 4:
+            raise _lib.FoodRecError("a PropGroup holds 1..4 graphs")
+        nb = [int(_L.fr_spmm_task_blocks(g.n_seg)) for g in self.graphs]
+        task = np.concatenate([np.full(n, t, dtype=np.int32) for t, n in enumerate(nb)])
+        blk = np.concatenate([np.arange(n, dtype=np.int32) for n in nb])
+        key = np.concatenate([(np.arange(n) + 0.5) / max(n, 1) for n in nb])
+        order = np.argsort(key, kind="stable")
+        self.n_blocks = int(task.size)
+        self.blk_map = torch.from_numpy(np.stack([task[order], blk[order]], 1).copy()).to(self.graphs[0].device)
+        self._T = None
+
+    @property
+    def T(self):
+        if self._T is None:
+            ts = [g.T for g in self.graphs]
+            if any(t is None for t in ts):
+                raise _lib.FoodRecError("a graph of the group has no transpose plan")
+            self._T = self if all(t is g for t, g in zip(ts, self.graphs)) else PropGroup(ts)
+        return self._T
+
+
+def spmm_grouped(group: PropGroup, Xs, Zs, alpha: float, beta: float, X1s=None, Z1s=None, outs=None):
+    """One launch: `out[t] = alpha * S_t @ [Xs[t]; X1s[t]] + beta * [Zs[t]; Z1s[t]]` for every graph of the group;
+    no autograd.  Bit-identical to the separate `spmm` calls."""
+    n = len(group.graphs)
+    X1s = X1s or [None] * n
+    Z1s = Z1s or [None] * n
+    d = Xs[0].shape[1]
+    given, outs, tasks = outs, [], (_lib.SpmmTask * n)()
+    prof = PROFILE
+    for t, g in enumerate(group.graphs):
+        X, X1, Z, Z1 = Xs[t], X1s[t], Zs[t], Z1s[t]
+        for a, name in ((X, "X"), (X1, "X1"), (Z, "Z"), (Z1, "Z1")):
+            if a is not None:
+                _chk_f32(a, name)
+        if X.shape[0] + (X1.shape[0] if X1 is not None else 0) != g.n_cols or X.shape[1] != d:
+            raise _lib.FoodRecError(f"task {t}: operand rows do not match the graph")
+        out = given[t] if given is not None else torch.empty((g.n_rows, d), dtype=torch.float32, device=X.device)
+        outs.append(out)
+        tk = tasks[t]
+        tk.seg, tk.n_seg, tk.long_rows, tk.n_long = g.seg.data_ptr(), g.n_seg, g.long_rows.data_ptr(), g.n_long
+        tk.col_idx, tk.val = g.col.data_ptr(), g.val.data_ptr()
+        tk.X0, tk.X1, tk.x_split = X.data_ptr(), _lib.ptr(X1), X.shape[0] if X1 is not None else 0
+        tk.Z0, tk.Z1 = _lib.ptr(Z), _lib.ptr(Z1)
+        tk.z_split = Z.shape[0] if (Z is not None and Z1 is not None) else 0
+        tk.alpha, tk.beta = float(alpha), float(beta)
+        tk.Y, tk.partial, tk.counters = out.data_ptr(), g.partial(d).data_ptr(), g.counters.data_ptr()
+    if prof is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _lib.check(_L.fr_spmm_csr_f32_grouped(tasks, n, d, group.blk_map.data_ptr(), group.n_blocks, _lib.stream_ptr()),
+               "fr_spmm_csr_f32_grouped")
+    if prof is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        prof.append((ev0, ev1, sum(g.spmm_bytes(d) for g in group.graphs), group, Zs[0] is not None))
+    return outs
+
+
+def _propagate_mean_grouped_raw(group, tops, bottoms, n_layers):
+    inv = 1.0 / (n_layers + 1)
+    t, t1 = list(tops), list(bottoms)
+    for layer in range(n_layers):
+        last = layer == n_layers - 1
+        t = spmm_grouped(group, t, list(tops), inv if last else 1.0, inv if last else 1.0, X1s=t1, Z1s=list(bottoms))
+        t1 = [None] * len(t)
+    return t
+
+
+class _PropagateMeanGrouped(torch.autograd.Function):
+    """Layer-mean propagation of `[top_t; bottom_t]` over graph t, all graphs of the group in one launch per layer
+    (forward and backward)."""
+
+    @staticmethod
+    def forward(ctx, group, n_layers, *tabs):
+        n = len(group.graphs)
+        tops, bottoms = [t.contiguous() for t in tabs[:n]], [t.contiguous() for t in tabs[n:]]
+        ctx.group, ctx.n_layers, ctx.n_top = group, n_layers, [t.shape[0] for t in tops]
+        return tuple(_propagate_mean_grouped_raw(group, tops, bottoms, n_layers))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gt = ctx.group.T
+        gs = list(gs)
+        d = next(g.shape[1] for g in gs if g is not None)
+        for k, g in enumerate(gs):
+            if g is None:      # an output nobody differentiated: its cotangent is zero
+                gr = ctx.group.graphs[k]
+                gs[k] = torch.zeros((gr.n_rows, d), dtype=torch.float32, device=gr.device)
+            else:
+                gs[k] = g.contiguous()
+                _take_mask(gs[k])          # the grouped launch does not use row masks; drop the registration
+        r = _propagate_mean_grouped_raw(gt, gs, [None] * len(gs), ctx.n_layers)
+        tops = [x[:nt] for x, nt in zip(r, ctx.n_top)]
+        bottoms = [x[nt:] for x, nt in zip(r, ctx.n_top)]
+        return (None, None, *tops, *bottoms)
+
+
+def propagate_mean_grouped(group: PropGroup, tops, bottoms, n_layers: int):
+    """Differentiable `mean_l S_t^l [tops[t]; bottoms[t]]` for every graph t of `group`, one launch per layer for the
+    whole group (CLUSSL's three item-side graphs, pricai_modelx.py:179-218)."""
+    if n_layers == 0:
+        return [torch.cat((a, b), 0) for a, b in zip(tops, bottoms)]
+    return list(_PropagateMeanGrouped.apply(group, n_layers, *tops, *bottoms))
+
+
 class _SpmmBiasTanh(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bias, graph):

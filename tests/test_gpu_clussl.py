@@ -92,3 +92,26 @@ def test_clussl_c1_vs_oracle():
     for name, p_ in m.named_parameters():
         if name in P:
             close(p_.grad, P[name].grad.numpy(), rtol=5e-4)
+
+
+def test_grouped_item_side_launch_equals_separate_streams(mini_ds, mini_batches):
+    """The grouped launch of the three item-side graphs (default) and the three launches on forked streams give the
+    same loss terms and gradients."""
+    from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
+    torch.manual_seed(999)
+    m = PRICAI_ModelX(cfg_for(mini_ds), mini_ds).to("cuda")
+    batch = dev_batch(mini_batches[0])
+    res = []
+    for grouped in (True, False):
+        m.group_item_graphs = grouped
+        m.zero_grad(set_to_none=True)
+        losses = m.calculate_loss(batch)
+        sum(losses).backward()
+        torch.cuda.synchronize()
+        res.append(([float(x) for x in losses], {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    # (the ranking loss scatters its gradient with fp32 atomics, so two runs of the SAME path already differ in the
+    # last bits; the propagation launches themselves are compared bit for bit in test_gpu_propagation.py)
+    close(torch.tensor(res[0][0]), np.asarray(res[1][0]), rtol=1e-6)
+    assert res[0][1].keys() == res[1][1].keys()
+    for n in res[0][1]:
+        close(res[0][1][n], res[1][1][n].cpu().numpy(), rtol=2e-6)

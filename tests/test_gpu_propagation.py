@@ -226,3 +226,51 @@ def test_push_epilogue_single_rank_matches_plain_propagation(mini_ds):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_grouped_launch_is_bit_identical_to_separate_launches():
+    """`fr_spmm_csr_f32_grouped`: three graphs of different sizes (ragged, long rows, an empty one among them) in one
+    grid, two-segment operands, fused `+ beta Z`; forward and backward through the layer-mean propagation."""
+    from foodrec_b200 import graph as G, ops
+    rng = np.random.default_rng(7)
+    specs = [(900, list(rng.integers(0, 30, size=900))),
+             (400, [3000, 129, 700] + list(rng.integers(0, 200, size=397))),
+             (64, [0] * 64)]
+    graphs, tops, bottoms = [], [], []
+    for k, (n, degs) in enumerate(specs):
+        degs = np.asarray(degs)
+        rp, col, val = random_csr(n, n, degs, 10 + k)
+        gt = G.PropGraph(*_transpose_csr(rp, col, val, n), n, "cuda")
+        g = G.PropGraph(rp, col, val, n, "cuda", transpose=gt)
+        gt.T = g
+        graphs.append(g)
+        n_top = n // 3
+        tops.append(torch.randn(n_top, 64, device="cuda", requires_grad=True))
+        bottoms.append(torch.randn(n - n_top, 64, device="cuda", requires_grad=True))
+    grp = ops.PropGroup(graphs)
+    assert grp.n_blocks == sum(-(-g.n_seg // 32) for g in graphs)
+    outs = ops.propagate_mean_grouped(grp, tops, bottoms, 2)
+    w = [torch.randn_like(o) for o in outs]
+    sum((o * wi).sum() for o, wi in zip(outs, w)).backward()
+    got = [(t.grad.clone(), b.grad.clone()) for t, b in zip(tops, bottoms)]
+    for t, b in zip(tops, bottoms):
+        t.grad = b.grad = None
+    prev = ops.USE_ROW_MASKS
+    ops.USE_ROW_MASKS = False
+    try:
+        ref = [ops.propagate_mean(g, t, 2, bottom=b) for g, t, b in zip(graphs, tops, bottoms)]
+        sum((o * wi).sum() for o, wi in zip(ref, w)).backward()
+    finally:
+        ops.USE_ROW_MASKS = prev
+    for o, r in zip(outs, ref):
+        assert torch.equal(o, r)
+    for (gt_, gb_), t, b in zip(got, tops, bottoms):
+        assert torch.equal(gt_, t.grad) and torch.equal(gb_, b.grad)
+    assert all(int(g.counters.abs().sum()) == 0 for g in graphs)
+
+
+def _transpose_csr(rp, col, val, n):
+    import scipy.sparse as sp
+    m = sp.csr_matrix((val, col, rp), shape=(n, n)).T.tocsr()
+    m.sort_indices()
+    return m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data.astype(np.float32)

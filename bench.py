@@ -833,7 +833,8 @@ def _bench_partitioned_propagation(dev, rank, world, barrier, peaks):
     out = {"workload": f"C5-shaped graph built on the device: {n_users} users, {n_items} items, {g.nnz} stored entries "
                        f"(symmetrised), d=64 table {n * d * 4 / 1e6:.0f} MB, {layers} layers fwd + bwd, layer mean; "
                        f"same total problem at every N (strong scaling)",
-           "world": world}
+           "world": world,
+           "partition": "rows dealt round-robin to the ranks (rank p owns rows p, p + N, ...): equal stored entries per rank"}
     if world == 1:
         e1 = ego.clone().requires_grad_(True)
 
@@ -853,7 +854,7 @@ def _bench_partitioned_propagation(dev, rank, world, barrier, peaks):
                                         "traffic": _hbm_traffic()})
         return out
     import torch.distributed as dist
-    pg = D.RowPartitionedGraph(g.row_ptr_host, g.col, g.val, n, rank, world, dev)
+    pg = D.RowPartitionedGraph(g.row_ptr_host, g.col, g.val, n, rank, world, dev, balance="interleave")
     nnz_local = pg.local.nnz
     del g
     el = pg.local_rows(ego).requires_grad_(True)

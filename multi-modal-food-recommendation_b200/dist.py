@@ -36,21 +36,50 @@ def shard_rows(n_rows: int, world: int):
 
 
 class RowPartitionedGraph:
-    """This rank's row block of a square normalised adjacency given as host CSR arrays."""
+    """This rank's row block of a square normalised adjacency given as CSR arrays (host numpy or torch tensors).
 
-    def __init__(self, row_ptr: np.ndarray, col: np.ndarray, val: np.ndarray, n_nodes: int, rank: int, world: int,
-                 device, symmetric: bool = True, graph_cls=PropGraph):
-        self.n_nodes, self.rank, self.world = n_nodes, rank, world
+    `balance="block"`: rank p owns the contiguous rows [p R, (p + 1) R).  With users numbered before items the blocks
+    hold very different numbers of stored entries (item rows are ~5x longer than user rows on the C5-shaped graph: the
+    slowest rank had 70 % of them at N = 2).  `balance="interleave"` relabels the nodes `new = (old % P) R + old // P`
+    -- rank p owns the rows p, p + P, p + 2P, ... -- so users and items, short rows and long rows, are dealt round-robin
+    and every rank gets ~1/P of the entries; the all-gather still moves equal contiguous blocks.  `local_rows` /
+    `to_original` convert between the original numbering and a rank's block / the gathered table."""
+
+    def __init__(self, row_ptr, col, val, n_nodes: int, rank: int, world: int, device, symmetric: bool = True,
+                 graph_cls=PropGraph, balance: str = "block"):
+        if balance not in ("block", "interleave"):
+            raise ValueError("balance must be 'block' or 'interleave'")
+        self.n_nodes, self.rank, self.world, self.balance = n_nodes, rank, world, balance
         self.rows_per_rank, self.n_padded = shard_rows(n_nodes, world)
-        lo = min(rank * self.rows_per_rank, n_nodes)
-        hi = min(lo + self.rows_per_rank, n_nodes)
-        self.lo, self.hi = lo, hi
+        R = self.rows_per_rank
         rp = np.asarray(row_ptr, dtype=np.int64)
-        local_rp = np.full(self.rows_per_rank + 1, rp[hi] - rp[lo], dtype=np.int64)
-        local_rp[:hi - lo + 1] = rp[lo:hi + 1] - rp[lo]
+        if balance == "block":
+            lo = min(rank * R, n_nodes)
+            hi = min(lo + R, n_nodes)
+            self.lo, self.hi = lo, hi
+            local_rp = np.full(R + 1, rp[hi] - rp[lo], dtype=np.int64)
+            local_rp[:hi - lo + 1] = rp[lo:hi + 1] - rp[lo]
+            lcol, lval = col[rp[lo]:rp[hi]], val[rp[lo]:rp[hi]]
+        else:
+            rows = np.arange(rank, n_nodes, world, dtype=np.int64)          # original ids of this rank's rows
+            self.lo, self.hi = 0, rows.size
+            deg = rp[rows + 1] - rp[rows]
+            local_rp = np.full(R + 1, int(deg.sum()), dtype=np.int64)
+            local_rp[0] = 0
+            np.cumsum(deg, out=local_rp[1:rows.size + 1])
+            tcol = col if torch.is_tensor(col) else torch.from_numpy(np.ascontiguousarray(col))
+            tval = val if torch.is_tensor(val) else torch.from_numpy(np.ascontiguousarray(val))
+            dv = tcol.device
+            t_deg = torch.from_numpy(deg).to(dv)
+            shift = torch.from_numpy(rp[rows] - local_rp[:rows.size]).to(dv)       # global offset - local offset, per row
+            elem = torch.repeat_interleave(shift, t_deg) + torch.arange(int(local_rp[-1]), device=dv)
+            c = tcol[elem].to(torch.int64)
+            lcol = ((c % world) * R + c // world).to(torch.int32)                    # position in the gathered table
+            lval = tval[elem]
+            if not torch.is_tensor(col):
+                lcol, lval = lcol.numpy(), lval.numpy()
         # columns index the all-gathered [n_padded, d] table; padding rows are empty
-        self.local = graph_cls(local_rp, col[rp[lo]:rp[hi]], val[rp[lo]:rp[hi]], self.n_padded, device,
-                               transpose="self" if symmetric else None)
+        self.local = graph_cls(local_rp, lcol, lval, self.n_padded, device, transpose="self" if symmetric else None)
         self.symmetric = symmetric
 
     @classmethod
@@ -58,10 +87,20 @@ class RowPartitionedGraph:
         return cls(g.row_ptr_host, g.col.cpu().numpy(), g.val.cpu().numpy(), g.n_rows, rank, world, device, **kw)
 
     def local_rows(self, full: torch.Tensor) -> torch.Tensor:
-        """This rank's (padded) row block of a full `[n_nodes, d]` table."""
+        """This rank's (padded) row block of a full `[n_nodes, d]` table in the ORIGINAL numbering."""
         out = torch.zeros((self.rows_per_rank, full.shape[1]), dtype=full.dtype, device=full.device)
-        out[:self.hi - self.lo] = full[self.lo:self.hi]
+        if self.balance == "block":
+            out[:self.hi - self.lo] = full[self.lo:self.hi]
+        else:
+            out[:self.hi] = full[self.rank::self.world]
         return out
+
+    def to_original(self, gathered: torch.Tensor) -> torch.Tensor:
+        """`[n_nodes, d]` table in the original numbering from the all-gathered `[n_padded, d]` blocks."""
+        if self.balance == "block":
+            return gathered[:self.n_nodes]
+        R, P = self.rows_per_rank, self.world
+        return gathered.view(P, R, -1).transpose(0, 1).reshape(P * R, -1)[:self.n_nodes]
 
 
 def _all_gather_rows(x_local: torch.Tensor, group=None) -> torch.Tensor:

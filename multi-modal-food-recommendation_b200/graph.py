@@ -53,6 +53,28 @@ class PropGraph:
         self._partial = {}
         self.T = self if transpose == "self" else transpose
 
+    @classmethod
+    def from_plan(cls, row_ptr, col, val, n_cols: int, device, seg, long_rows, counts, symmetric: bool = False):
+        """Adopt a stored segment plan (`cache.load_graph`) instead of rebuilding it from the row pointers."""
+        self = cls.__new__(cls)
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        self.n_rows, self.n_cols, self.nnz = int(row_ptr.shape[0] - 1), int(n_cols), int(row_ptr[-1])
+        self.device = dev = torch.device(device)
+        self.row_ptr_host = row_ptr
+        self.n_seg, self.n_long, self.n_part = (int(c) for c in counts)
+        self.seg_host = np.ascontiguousarray(seg, dtype=np.int32).reshape(-1, 4)
+        self.long_rows_host = np.ascontiguousarray(long_rows, dtype=np.int32).reshape(-1, 4)
+        if self.seg_host.shape[0] < max(self.n_seg, 1) or self.long_rows_host.shape[0] < max(self.n_long, 1):
+            raise _lib.FoodRecError("stored segment plan is shorter than its counts")
+        def up(a, dt):           # (memory-mapped inputs are read-only: copy before handing them to torch)
+            return torch.from_numpy(np.array(a, dtype=dt, copy=True)).to(dev)
+        self.col, self.val = up(col, np.int32), up(val, np.float32)
+        self.seg, self.long_rows = up(self.seg_host, np.int32), up(self.long_rows_host, np.int32)
+        self.counters = torch.zeros(max(self.n_long, 1), dtype=torch.int32, device=dev)
+        self._partial = {}
+        self.T = self if symmetric else None
+        return self
+
     def partial(self, d: int) -> torch.Tensor:
         buf = self._partial.get(d)
         if buf is None:

@@ -231,6 +231,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="headline + eval only (skip C4, partitioned propagation, kNN, baselines)")
     ap.add_argument("--eager", action="store_true", help="drop-in eager step (no CUDA graph)")
     ap.add_argument("--foreach-adam", action="store_true", help="torch's default foreach Adam instead of fused=True")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused=True) instead of this library's fr_adam_step")
     ap.add_argument("--min-timed-s", type=float, default=0.5, help="the timed region replays at least this long")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -285,8 +286,12 @@ def main():
     model.train()
     # trainer.py:142-143 builds optim.Adam(params, lr, weight_decay).  Same optimizer, torch's fused
     # multi-tensor implementation (one launch instead of ~15), capturable so the step stays on the device.
-    opt = torch.optim.Adam(model.parameters(), lr=cfg["learning_rate"], weight_decay=0.0,
-                           capturable=not args.eager, fused=not args.foreach_adam)
+    if args.torch_adam or args.foreach_adam:
+        opt = torch.optim.Adam(model.parameters(), lr=cfg["learning_rate"], weight_decay=0.0,
+                               capturable=not args.eager, fused=not args.foreach_adam)
+    else:   # the same update as one multi-tensor launch of this library (train.FusedAdam, fr_adam_step)
+        from foodrec_b200.train import FusedAdam
+        opt = FusedAdam(model.parameters(), lr=cfg["learning_rate"])
     # weak scaling: every rank trains on its own batches of the replicated graph (multi-GPU)
     host_batches = sample_train_batches(ds, BATCH, 64, seed=7 + rank)
     keys = ("u_id", "pos_i_id", "neg_i_id")
@@ -498,6 +503,8 @@ def main():
     if world == 1 and not args.no_schgn:
         torch.set_num_threads(os.cpu_count() or 1)
         line["schgn"] = _bench_schgn(ds, dev, steps_per_epoch, not args.no_cpu_baseline)
+    if world == 1 and not args.no_extras:
+        line["healthrec"] = _bench_healthrec(ds, dev, steps_per_epoch, peaks)
     if world == 1 and not args.no_extras:
         line["torch_cuda_baseline"] = _bench_torch_cuda(ds, sd0, cfg, host_batches, dev, steps_per_epoch, ms_dev, ev, model)
     if world == 1 and not args.no_cpu_baseline:
@@ -1016,6 +1023,46 @@ def _bench_torch_cuda(ds, sd0, cfg, host_batches, dev, steps_per_epoch, ms_ours,
     out["full_sort_eval"] = {"ms": ms_e, "users_per_s": ds.n_users / (ms_e * 1e-3), "this_library_ms": ev["ms_dev"],
                              "speedup": ms_e / ev["ms_dev"],
                              "what": "fp32 matmul + history mask + torch.topk(20) in blocks of 8192 users"}
+    return out
+
+
+def _bench_healthrec(ds, dev, steps_per_epoch, peaks):
+    """HealthRec (`CIKM_Model`) on the same C2 data -- 2 + 1 propagation layers, BPR / KD / health terms,
+    and dense Adam over ~200 M parameters, most of them the trainable raw-feature tables (cikm_model.py:83,87).  Two
+    graph-replayed steps: this library's formulation (rows gathered before the feature projections, `fr_adam_step`)
+    and the reference's (all-item projections at cikm_model.py:240-243, torch's fused Adam) on the same kernels otherwise."""
+    from foodrec_b200.models.cikm_model import CIKM_Model
+    from foodrec_b200.synth import sample_train_batches
+    from foodrec_b200.train import FusedAdam, GraphedTrainStep
+    cfg = Cfg(device=str(dev), embedding_size=64, train_batch_size=BATCH, is_multimodal_model=True, end2end=False,
+              use_health_level_multi_hot=True, num_attention_heads=2, num_hidden_layers=2, attention_probs_dropout_prob=0.5,
+              hidden_act="gelu", n_layers=2, ui_layers=1, reg_weight=0.5, loss_kd=0.05, loss_health=0.1, kd_threshold=0.4,
+              learning_rate=0.001)          # configs/model/CIKM_Model.yaml
+    bs = sample_train_batches(ds, BATCH, 4, seed=21)
+    res = [{k: torch.from_numpy(np.asarray(v)).to(dev) for k, v in b.items()} for b in bs]
+    out = {}
+    for name, all_items, own_adam in (("this_library", False, True), ("reference_formulation", True, False)):
+        torch.manual_seed(999)
+        m = CIKM_Model(cfg, ds).to(dev)
+        m.train()
+        m.project_all_items = all_items
+        n_par = sum(p.numel() for p in m.parameters() if p.requires_grad)
+        opt = (FusedAdam(m.parameters(), lr=cfg["learning_rate"]) if own_adam
+               else torch.optim.Adam(m.parameters(), lr=cfg["learning_rate"], fused=True, capturable=True))
+        step = GraphedTrainStep(m, opt, res[0])
+        it = iter(range(10 ** 9))
+        ms = timed_ms(lambda: step(res[next(it) % 4]), 30, warm=5)
+        a_ms = timed_graph_ms(opt.step, 5)
+        out[name] = {"ms_per_step": ms, "epochs_per_s": 1.0 / (steps_per_epoch * ms * 1e-3),
+                     "adam": {"ms": a_ms, "parameters": n_par, "bytes": 28 * n_par,
+                              "achieved_GBs": 28 * n_par / (a_ms * 1e-3) / 1e9, "frac_of_hbm_peak": 28 * n_par / (a_ms * 1e-3) / 1e9 / peaks[0],
+                              "kernel": "adam_multi_kernel (fr_adam_step)" if own_adam else "torch.optim.Adam(fused=True)"},
+                     "projection": "rows gathered first: [2B, Dv] x [Dv, 64]" if not all_items else "all items: [I, Dv] x [Dv, 64]"}
+        del m, opt, step
+        torch.cuda.empty_cache()
+    out["workload"] = (f"HealthRec (CIKM_Model) train step on the C2 data, B={BATCH}: item-ingredient propagation x2 + user-item x1, "
+                       f"transformer / attention / health head in torch, BPR + EmbLoss + KD fused, dense Adam")
+    out["speedup_vs_reference_formulation"] = out["reference_formulation"]["ms_per_step"] / out["this_library"]["ms_per_step"]
     return out
 
 

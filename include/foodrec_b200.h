@@ -305,6 +305,25 @@ int fr_spmm_csr_f32_push(const int32_t *seg, int64_t n_seg, const int32_t *long_
                          float beta, float *Y, float *partial, int32_t *counters, float *const *peers_host,
                          int32_t n_peers, int64_t row_off, void *stream);
 
+/* Dense Adam over many tensors in one launch (plus a one-thread prologue that advances the device-side step counter
+ * and derives the bias corrections, so the pair replays inside a CUDA graph).  Replaces `optim.Adam(...).step()` of
+ * FoodRec/common/trainer.py:144,205 with torch.optim.Adam's arithmetic (amsgrad = False, weight_decay = 0); dense on
+ * purpose: rows with a zero gradient still move while their first moment decays.  HealthRec's trainable raw-feature
+ * tables (cikm_model.py:83,87) make this the largest HBM stream of its step.
+ * Hyper-parameters are doubles like torch's python floats: `1 - beta` is formed in double and then rounded to fp32.
+ *   step_dev    device int32, the number of steps taken so far (incremented by the call)
+ *   scalars_dev device float[2] scratch */
+#define FR_ADAM_MAX_TENSORS 64
+typedef struct fr_adam_tensor {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    int64_t n;
+} fr_adam_tensor;
+int fr_adam_step(const fr_adam_tensor *tensors_host, int32_t n_tensors, double lr, double beta1, double beta2, double eps,
+                 int32_t *step_dev, float *scalars_dev, void *stream);
+
 /* Measurement probe (not on the product path): gathers `n_idx` rows of a d = 64 table and does nothing else;
  * its bytes/s is the gather roofline the propagation kernel is compared with (scripts/microbench_gather_roofline.py).
  * out: blocks * 32 floats of scratch. */

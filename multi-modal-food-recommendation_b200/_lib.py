@@ -42,6 +42,7 @@ SIGNATURES = {
                                         _p, _p, _p, _p]),
     "fr_spmm_task_blocks": (_i64, [_i64]),
     "fr_spmm_csr_f32_grouped": (C.c_int, [_p, _i32, _i32, _p, _i64, _p]),
+    "fr_adam_step": (C.c_int, [_p, _i32, C.c_double, C.c_double, C.c_double, C.c_double, _p, _p, _p]),
     "fr_rank_loss_ws_floats": (_i64, []),
     "fr_rank_loss_fwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
     "fr_rank_loss_bwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _p]),
@@ -83,6 +84,11 @@ class SpmmTask(C.Structure):
     _fields_ = [("seg", _p), ("n_seg", _i64), ("long_rows", _p), ("n_long", _i64), ("col_idx", _p), ("val", _p),
                 ("X0", _p), ("X1", _p), ("x_split", _i32), ("Z0", _p), ("Z1", _p), ("z_split", _i32),
                 ("alpha", _f32), ("beta", _f32), ("Y", _p), ("partial", _p), ("counters", _p)]
+
+
+class AdamTensor(C.Structure):
+    """`fr_adam_tensor` of include/foodrec_b200.h."""
+    _fields_ = [("param", _p), ("grad", _p), ("exp_avg", _p), ("exp_avg_sq", _p), ("n", _i64)]
 
 
 for _name, (_res, _args) in SIGNATURES.items():

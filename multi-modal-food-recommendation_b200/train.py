@@ -73,6 +73,51 @@ class OverlappedGradAllReduce:
             h.remove()
 
 
+class FusedAdam(torch.optim.Optimizer):
+    """`torch.optim.Adam(params, lr, betas, eps)` (amsgrad = False, weight_decay = 0: the reference's optimizer,
+    FoodRec/common/trainer.py:144) as ONE multi-tensor launch of this library (`fr_adam_step`): dense update of every
+    parameter that has a gradient, step counter on the device, capturable in a CUDA graph.  State keys (`exp_avg`,
+    `exp_avg_sq`) are those of torch's Adam, so optimizer checkpoints carry over except for `step`."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._dev_state = {}
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import _lib
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            dev = ps[0].device
+            if dev.type != "cuda":
+                raise _lib.FoodRecError("FusedAdam needs CUDA parameters (foodrec_b200 has no CPU path)")
+            ds = self._dev_state.get(gi)
+            if ds is None:
+                ds = self._dev_state[gi] = (torch.zeros(1, dtype=torch.int32, device=dev),
+                                            torch.zeros(2, dtype=torch.float32, device=dev))
+            tensors = (_lib.AdamTensor * len(ps))()
+            for t, p in zip(tensors, ps):
+                if p.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
+                    raise _lib.FoodRecError("FusedAdam handles contiguous fp32 parameters with dense gradients")
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                t.param, t.grad, t.exp_avg, t.exp_avg_sq = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                t.n = p.numel()
+            b1, b2 = group["betas"]
+            _lib.check(_lib.lib.fr_adam_step(tensors, len(ps), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                             ds[0].data_ptr(), ds[1].data_ptr(), _lib.stream_ptr()), "fr_adam_step")
+        return loss
+
+
 class GraphedTrainStep:
     """Capture `zero_grad -> calculate_loss -> backward -> optimizer.step` once, replay per batch.
 

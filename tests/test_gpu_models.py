@@ -160,3 +160,27 @@ def test_model_level_full_sort_evaluation_metrics(masked):
     # index-level: differences only where the fp32 scores tie (GPU vs CPU propagation differ by ~1e-7)
     diff = top != ref_top.numpy()
     assert diff.mean() < 2e-3
+
+
+def test_healthrec_gather_first_projection_equals_all_item_projection(mini_ds, mini_batches):
+    """HealthRec's raw-feature projections: gathering the 2B consumed rows before `image_trs` / `text_trs` (default)
+    gives the loss terms and the DENSE gradients of the reference's all-item projection (cikm_model.py:240-244)."""
+    from foodrec_b200.models.cikm_model import CIKM_Model
+    m, _ = load(CIKM_Model, "healthrec_mini.npz", mini_ds, n_layers=2, ui_layers=1, reg_weight=0.5, loss_kd=0.05,
+                loss_health=0.1, kd_threshold=0.4)
+    m.eval()                                     # dropout off, so both formulations are deterministic
+    batch = dev_batch(mini_batches[0])
+    out = []
+    for all_items in (False, True):
+        m.project_all_items = all_items
+        m.zero_grad(set_to_none=True)
+        losses = m.calculate_loss(batch)
+        sum(losses).backward()
+        out.append(([float(x) for x in losses], {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    assert out[0][1].keys() == out[1][1].keys()
+    for a, b in zip(out[0][0], out[1][0]):
+        assert abs(a - b) <= 1e-6 * max(abs(b), 1e-12)
+    for n in out[0][1]:
+        a, b = out[0][1][n], out[1][1][n]
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 2e-5 * max(float(b.abs().max()), 1e-12), n

@@ -210,3 +210,52 @@ def test_item_views_refuses_a_split_backward():
     (mf + cl.sum() + reg.sum()).backward()
     for x, y in zip(g1, [p.grad for p in m.parameters() if p.grad is not None]):
         assert torch.allclose(x, y, rtol=1e-5, atol=1e-9)
+
+
+def test_fused_adam_follows_torch_adam_and_replays_in_a_graph():
+    """`fr_adam_step` (one multi-tensor launch, device-side step counter) against torch.optim.Adam over ragged tensor
+    sizes (vector path, scalar tails, an unaligned view), ten steps; then the same update captured in a CUDA graph."""
+    from foodrec_b200.train import FusedAdam
+    torch.manual_seed(3)
+    shapes = [(4097, 64), (3,), (1000, 7), (64, 64), (5, 4096), (1,)]
+    base = [torch.randn(s, device="cuda") for s in shapes]
+    big = torch.randn(10_001, device="cuda")
+    base.append(big[1:])                      # 4-byte-aligned only: the kernel's scalar path
+    ref_p = [torch.nn.Parameter(b.clone()) for b in base]
+    my_p = [torch.nn.Parameter(b.clone()) for b in base]
+    ref = torch.optim.Adam(ref_p, lr=2e-3, betas=(0.9, 0.999), eps=1e-8)
+    mine = FusedAdam(my_p, lr=2e-3, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(10):
+        for a, b in zip(ref_p, my_p):
+            g = torch.randn_like(a) * (0.0 if step == 4 else 1.0)          # one all-zero gradient step: rows still move
+            if step % 3 == 0:
+                g[: g.shape[0] // 2] = 0                                  # and partially zero gradients
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step()
+        mine.step()
+        for a, b in zip(ref_p, my_p):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (step, float((a - b).abs().max()))
+    for a, b in zip(ref_p, my_p):
+        assert torch.allclose(ref.state[a]["exp_avg"], mine.state[b]["exp_avg"], rtol=2e-6, atol=1e-6)       # values are O(1)
+        assert torch.allclose(ref.state[a]["exp_avg_sq"], mine.state[b]["exp_avg_sq"], rtol=2e-6, atol=1e-7)
+    # graph capture: static gradient buffers, three replays == three more torch steps
+    gs = [torch.randn_like(p) for p in my_p]
+    for b, g in zip(my_p, gs):
+        b.grad = g
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph):
+        mine.step()
+    before = [p.detach().clone() for p in my_p]       # capture does not execute
+    for _ in range(3):
+        graph.replay()
+    for a, g in zip(ref_p, gs):
+        a.grad = g.clone()
+    for _ in range(3):
+        ref.step()
+    torch.cuda.synchronize()
+    for a, b, b0 in zip(ref_p, my_p, before):
+        assert not torch.equal(b, b0)
+        assert torch.allclose(a, b, rtol=3e-6, atol=1e-7), float((a - b).abs().max())

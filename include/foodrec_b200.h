@@ -194,7 +194,9 @@ int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, const int64_
 int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
                 const int32_t *pairs_host, int32_t P, const float *Dm, const float *rowmean,
                 const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host,
-                uint8_t *const *mask_host /* optional: mark the rows idx[] of each table's mask */, void *stream);
+                uint8_t *const *mask_host /* optional: mark the rows idx[] of each table's mask */,
+                float *ws /* fr_dcor_bwd_ws_floats(n) floats of scratch, 16-byte aligned */, void *stream);
+int64_t fr_dcor_bwd_ws_floats(int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * Ranking: scores = scale * A . B^T + bias  ->  per-row top-k, never materialising [M, N].

@@ -51,7 +51,8 @@ SIGNATURES = {
     "fr_dcor_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p, _p, _p]),
     "fr_sum_rows": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
     "fr_spread_rows": (C.c_int, [_p, _i32, _i64, _p, _p, _i32, _i32, _p, _p, _p]),
-    "fr_dcor_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fr_dcor_bwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fr_dcor_bwd_ws_floats": (_i64, [_i32]),
     "fr_f32_to_bf16": (C.c_int, [_p, _p, _i64, _i32, _i32, _p]),
     "fr_gemm_topk_ws_bytes": (_i64, [_i32]),
     "fr_gemm_topk_bf16": (C.c_int, [_p, _i32, _p, _i32, _i32, _f32, _p, _p, _p, _p, _i32, _p, _p, _p, _i64, _p]),

@@ -9,8 +9,8 @@
 //   dcor_dot_kernel     s_vw = sum_ij A_v A_w / n^2 for all view pairs with A = double-centred D
 //                       (never stored), block partials folded in fixed order by the last block,
 //                       which also emits dcor_p and the partial derivatives d dcor_p / d s_xy
-//   dcor_bwd_kernel     dX_v = 4 (diag(W 1) X - W X),  W = (sum_w C_vw A_w) / (2 D_v) off-diagonal,
-//                       scatter-added straight into the dense table gradients.
+//   dcor_w_kernel       W = (sum_w C_vw A_w) / (2 D_v) off-diagonal and its row sums
+//   dcor_wx_kernel      dX_v = 4 (diag(W 1) X - W X), scatter-added straight into the dense table gradients.
 // The double-centred matrices are projections (P A P = A), so the gradient w.r.t. D_v needs no
 // re-centring; the diagonal of D (mathematically constant) is dropped analytically instead of being
 // left to cancel numerically as autograd does.  n = 2B = 1024, d = 64: latency-bound, all in L2.
@@ -226,105 +226,161 @@ dcor_dot_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const doub
 }
 
 // ---------------------------------------------------------------------------------------- K3
-template <int D>
+// Backward in two launches (one kernel that interleaved the W computation with the product spent its time in chains of
+// dependent gathers at two CTAs per SM: 72 us at n = 1024; profiles/r2_dcor_bwd_*):
+//   dcor_w_kernel     W_v[i][j] = (sum_u C_vu A_u[i][j]) / (2 D_v[i][j]) off the diagonal (0 on it and where D_v == sqrt(eps),
+//                     i.e. duplicate rows: the analytic value), and the row sums  wsum_v[i]; one pass over the three distance
+//                     matrices, fully coalesced, 4 rows per CTA
+//   dcor_wx_kernel    dX_v[idx[i]] += 4 (wsum_v[i] x_i - sum_j W_v[i][j] x_j): a batched 32 x D x n product per CTA with the
+//                     column range split over blockIdx.z, register-prefetched operand tiles, float4 atomics into the dense
+//                     table gradients
 __global__ void __launch_bounds__(kThreads)
-dcor_bwd_kernel(Views vw, Pairs pr, const int64_t *__restrict__ idx, int n, const float *__restrict__ Dm,
-                const float *__restrict__ rowmean, const float *__restrict__ gm, const float *__restrict__ dfds,
-                const float *__restrict__ g_out) {
-    constexpr int RB = 16, JT = 64, KQ = D / 4;          // 16 rows x (D/4) float4 columns per CTA
-    static_assert(RB * KQ <= kThreads && (RB * JT) % kThreads == 0, "tile/threads mismatch");
-    __shared__ float Ws[RB][JT + 1];
-    __shared__ __align__(16) float Xs[JT][D];
-    __shared__ float Cm[kMaxV];
+dcor_w_kernel(int V, Pairs pr, int n, const float *__restrict__ Dm, const float *__restrict__ rowmean,
+              const float *__restrict__ gm, const float *__restrict__ dfds, const float *__restrict__ g_out,
+              float *__restrict__ W, float *__restrict__ wsum) {
+    __shared__ float Cm[kMaxV][kMaxV];
     __shared__ float gms[kMaxV];
-    const int v = blockIdx.y;
-    if (vw.dtab[v] == nullptr) return;
+    __shared__ float red[kThreads / 32];
     if (threadIdx.x == 0) {
         // C_vw: coefficient of A_w in d(sum_p g_p dcor_p) / d D_v
-        float c[kMaxV] = {0.f, 0.f, 0.f};
+        float c[kMaxV][kMaxV] = {};
         const float inv = 1.f / ((float)n * (float)n);
         for (int p = 0; p < pr.P; ++p) {
             const float g = __ldg(g_out + p);
             const int a = pr.a[p], b = pr.b[p];
-            if (a == v) { c[b] += g * dfds[p * 3 + 0] * inv; c[a] += 2.f * g * dfds[p * 3 + 1] * inv; }
-            if (b == v) { c[a] += g * dfds[p * 3 + 0] * inv; c[b] += 2.f * g * dfds[p * 3 + 2] * inv; }
+            c[a][b] += g * dfds[p * 3 + 0] * inv;
+            c[a][a] += 2.f * g * dfds[p * 3 + 1] * inv;
+            c[b][a] += g * dfds[p * 3 + 0] * inv;
+            c[b][b] += 2.f * g * dfds[p * 3 + 2] * inv;
         }
-        for (int w = 0; w < kMaxV; ++w) { Cm[w] = c[w]; gms[w] = w < vw.V ? gm[w] : 0.f; }
+        for (int v = 0; v < kMaxV; ++v) {
+            gms[v] = v < V ? gm[v] : 0.f;
+            for (int w = 0; w < kMaxV; ++w) Cm[v][w] = c[v][w];
+        }
     }
     __syncthreads();
-    const int i0 = blockIdx.x * RB;
-    const float *__restrict__ tab = vw.tab[v];
-    const float *__restrict__ Dv = Dm + (size_t)v * n * n;
-    // the column range is split over blockIdx.z; the result is linear in (wsum, acc), so every CTA adds
-    // its own 4 (wsum x_i - acc) into the dense gradient
-    const int jt_total = (n + JT - 1) / JT, jt_per = (jt_total + gridDim.z - 1) / gridDim.z;
-    const int j_lo = blockIdx.z * jt_per * JT, j_hi = min(n, (int)(blockIdx.z + 1) * jt_per * JT);
-    const int orow = threadIdx.x / KQ, okq = threadIdx.x % KQ;  // output element owned in the GEMM phase
-    const bool owner = threadIdx.x < RB * KQ;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float wsum = 0.f;
     const float eps_d = sqrtf(kEpsD);
-    for (int j0 = j_lo; j0 < j_hi; j0 += JT) {
-        // X_j tile (gathered rows), coalesced float4
-        for (int t = threadIdx.x; t < JT * KQ; t += kThreads) {
-            const int r = t / KQ, q = t - r * KQ;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j0 + r < n) x = fr::ldg_f4(tab + (size_t)idx[j0 + r] * D + 4 * q);
-            *reinterpret_cast<float4 *>(&Xs[r][4 * q]) = x;
-        }
-        // W tile: all loads of a thread's four elements are issued before any is used
-        {
-            float du[RB * JT / kThreads][kMaxV], rmj[RB * JT / kThreads][kMaxV], rmi[RB * JT / kThreads][kMaxV];
+    const int i0 = blockIdx.x * kRB2;
+    for (int r = 0; r < kRB2 && i0 + r < n; ++r) {
+        const int i = i0 + r;
+        float rmi[kMaxV], ws[kMaxV] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int e = 0; e < RB * JT / kThreads; ++e) {
-                const int t = threadIdx.x + e * kThreads;
-                const int r = t / JT, c = t - r * JT;
-                const int i = min(i0 + r, n - 1), j = min(j0 + c, n - 1);
+        for (int u = 0; u < kMaxV; ++u) rmi[u] = u < V ? __ldg(rowmean + (size_t)u * n + i) : 0.f;
+#pragma unroll 2
+        for (int j = threadIdx.x; j < n; j += kThreads) {
+            float d[kMaxV], A[kMaxV];
 #pragma unroll
-                for (int u = 0; u < kMaxV; ++u) {
-                    const bool on = u < vw.V;
-                    du[e][u] = on ? __ldg(Dm + ((size_t)u * n + i) * n + j) : 0.f;
-                    rmj[e][u] = on ? __ldg(rowmean + (size_t)u * n + j) : 0.f;
-                    rmi[e][u] = on ? __ldg(rowmean + (size_t)u * n + i) : 0.f;
-                }
+            for (int u = 0; u < kMaxV; ++u) {
+                d[u] = u < V ? __ldg(Dm + ((size_t)u * n + i) * n + j) : 1.f;
+                A[u] = u < V ? ((d[u] - __ldg(rowmean + (size_t)u * n + j)) - rmi[u]) + gms[u] : 0.f;
             }
 #pragma unroll
-            for (int e = 0; e < RB * JT / kThreads; ++e) {
-                const int t = threadIdx.x + e * kThreads;
-                const int r = t / JT, c = t - r * JT;
-                const int i = i0 + r, j = j0 + c;
-                float w = 0.f;
-                float dv = 0.f, g = 0.f;
+            for (int v = 0; v < kMaxV; ++v) {
+                if (v < V) {
+                    float g = 0.f;
 #pragma unroll
-                for (int u = 0; u < kMaxV; ++u) {
-                    if (u == v) dv = du[e][u];
-                    g = fmaf(Cm[u], ((du[e][u] - rmj[e][u]) - rmi[e][u]) + gms[u], g);
+                    for (int u = 0; u < kMaxV; ++u) g = fmaf(Cm[v][u], A[u], g);
+                    const float w = (i != j && d[v] > eps_d) ? g / (2.f * d[v]) : 0.f;
+                    W[((size_t)v * n + i) * n + j] = w;
+                    ws[v] += w;
                 }
-                if (i < n && j < j_hi && i != j && dv > eps_d) w = g / (2.f * dv);
-                Ws[r][c] = w;
             }
         }
+        for (int v = 0; v < V; ++v) {
+            const float t = block_sum(ws[v], red);
+            if (threadIdx.x == 0) wsum[(size_t)v * n + i] = t;
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+dcor_wx_kernel(Views vw, const int64_t *__restrict__ idx, int n, const float *__restrict__ W,
+               const float *__restrict__ wsum) {
+    constexpr int RB = 32, JT = 32, KQ = D / 4;           // 32 rows x (D/4) float4 columns per CTA, 32 columns of W per step
+    constexpr int RPT = RB * KQ / kThreads;               // output rows per thread (D = 64: 2, D = 32: 1)
+    static_assert(RB * KQ % kThreads == 0 && RB * JT == 4 * kThreads && JT * KQ <= 2 * kThreads, "tile/threads mismatch");
+    __shared__ __align__(16) float Ws[2][RB][JT + 4];
+    __shared__ __align__(16) float Xs[2][JT][D];
+    const int v = blockIdx.y;
+    float *__restrict__ dtab = vw.dtab[v];
+    if (dtab == nullptr) return;
+    const float *__restrict__ tab = vw.tab[v];
+    const float *__restrict__ Wv = W + (size_t)v * n * n;
+    const int i0 = blockIdx.x * RB;
+    const int jt_total = (n + JT - 1) / JT, jt_per = (jt_total + gridDim.z - 1) / gridDim.z;
+    const int jt_lo = blockIdx.z * jt_per, jt_hi = min(jt_total, jt_lo + jt_per);
+    const int okq = threadIdx.x % KQ, orow = (threadIdx.x / KQ) * RPT;      // this thread's float4 column and first row
+    // operand loads of one step: W tile RB x JT = 1024 floats (one float4 per thread), X tile JT x D (<= 2 float4 per thread)
+    const int wr = threadIdx.x / (JT / 4), wc = (threadIdx.x % (JT / 4)) * 4;
+    float4 wreg, xreg[2];
+    auto fetch = [&](int jt) {
+        const int j0 = jt * JT;
+        const int i = i0 + wr;
+        wreg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            if (j0 + wc + 3 < n && (n & 3) == 0) wreg = fr::ldg_f4(Wv + (size_t)i * n + j0 + wc);
+            else {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int e = 0; e < 4; ++e)
+                    if (j0 + wc + e < n) t[e] = __ldg(Wv + (size_t)i * n + j0 + wc + e);
+                wreg = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int t = threadIdx.x + e * kThreads;
+            xreg[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < JT * KQ) {
+                const int r = t / KQ, q = t % KQ;
+                if (j0 + r < n) xreg[e] = fr::ldg_f4(tab + (size_t)__ldg(idx + j0 + r) * D + 4 * q);
+            }
+        }
+    };
+    auto stash = [&](int buf) {
+        *reinterpret_cast<float4 *>(&Ws[buf][wr][wc]) = wreg;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int t = threadIdx.x + e * kThreads;
+            if (t < JT * KQ) *reinterpret_cast<float4 *>(&Xs[buf][t / KQ][4 * (t % KQ)]) = xreg[e];
+        }
+    };
+    float4 acc[RPT];
+#pragma unroll
+    for (int a = 0; a < RPT; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (jt_lo < jt_hi) {
+        fetch(jt_lo);
+        stash(0);
         __syncthreads();
-        if (owner) {
+        for (int jt = jt_lo; jt < jt_hi; ++jt) {
+            const int buf = (jt - jt_lo) & 1;
+            if (jt + 1 < jt_hi) fetch(jt + 1);              // next step's operands travel while this one is multiplied
 #pragma unroll 8
             for (int c = 0; c < JT; ++c) {
-                const float w = Ws[orow][c];
-                const float4 x = *reinterpret_cast<const float4 *>(&Xs[c][4 * okq]);
-                fr::fma4(acc, w, x);
-                wsum += w;
+                const float4 x = *reinterpret_cast<const float4 *>(&Xs[buf][c][4 * okq]);
+#pragma unroll
+                for (int a = 0; a < RPT; ++a) fr::fma4(acc[a], Ws[buf][orow + a][c], x);
             }
+            if (jt + 1 < jt_hi) stash(buf ^ 1);
+            __syncthreads();
         }
-        __syncthreads();
     }
-    if (owner && i0 + orow < n) {
-        const size_t row = (size_t)idx[i0 + orow];
-        const float4 xi = fr::ldg_f4(tab + row * D + 4 * okq);
-        float *dst = vw.dtab[v] + row * D + 4 * okq;
-        if (vw.mask[v] != nullptr && okq == 0) vw.mask[v][row] = 1;
-        atomicAdd(dst + 0, 4.f * (wsum * xi.x - acc.x));
-        atomicAdd(dst + 1, 4.f * (wsum * xi.y - acc.y));
-        atomicAdd(dst + 2, 4.f * (wsum * xi.z - acc.z));
-        atomicAdd(dst + 3, 4.f * (wsum * xi.w - acc.w));
+#pragma unroll
+    for (int a = 0; a < RPT; ++a) {
+        const int i = i0 + orow + a;
+        if (i >= n) continue;
+        const size_t row = (size_t)__ldg(idx + i);
+        float4 o = make_float4(-4.f * acc[a].x, -4.f * acc[a].y, -4.f * acc[a].z, -4.f * acc[a].w);
+        if (blockIdx.z == 0) {       // the diag(W 1) X term once per row
+            const float w4 = 4.f * __ldg(wsum + (size_t)v * n + i);
+            const float4 xi = fr::ldg_f4(tab + row * D + 4 * okq);
+            o.x = fmaf(w4, xi.x, o.x);
+            o.y = fmaf(w4, xi.y, o.y);
+            o.z = fmaf(w4, xi.z, o.z);
+            o.w = fmaf(w4, xi.w, o.w);
+            if (vw.mask[v] != nullptr && okq == 0) vw.mask[v][row] = 1;
+        }
+        atomicAdd(reinterpret_cast<float4 *>(dtab + row * D + 4 * okq), o);
     }
 }
 
@@ -388,21 +444,32 @@ extern "C" int fr_dcor_fwd(const float *const *tab_host, int32_t V, int32_t d, c
     return fr::check_launch("fr_dcor_fwd/dot");
 }
 
+extern "C" int64_t fr_dcor_bwd_ws_floats(int32_t n) { return (int64_t)kMaxV * n * n + (int64_t)kMaxV * n; }
+
 extern "C" int fr_dcor_bwd(const float *const *tab_host, int32_t V, int32_t d, const int64_t *idx, int32_t n,
                            const int32_t *pairs_host, int32_t P, const float *Dm, const float *rowmean,
                            const float *dfds, const float *gm, const float *g_out, float *const *d_tab_host,
-                           uint8_t *const *mask_host, void *stream) {
-    FR_REQUIRE(idx && Dm && rowmean && dfds && gm && g_out && d_tab_host && n > 0, "fr_dcor_bwd: bad argument");
+                           uint8_t *const *mask_host, float *ws, void *stream) {
+    FR_REQUIRE(idx && Dm && rowmean && dfds && gm && g_out && d_tab_host && ws && n > 0, "fr_dcor_bwd: bad argument");
+    FR_REQUIRE(((uintptr_t)ws & 15) == 0, "fr_dcor_bwd: workspace must be 16-byte aligned");
     Views vw;
     Pairs pr;
     if (int rc = fill(vw, pr, V, tab_host, d_tab_host, P, pairs_host)) return rc;
+    for (int v = 0; v < V; ++v)
+        FR_REQUIRE(vw.dtab[v] == nullptr || ((uintptr_t)vw.dtab[v] & 15) == 0, "fr_dcor_bwd: gradient tables must be 16-byte aligned");
     if (mask_host)
         for (int v = 0; v < V; ++v) vw.mask[v] = mask_host[v];
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 g((n + 15) / 16, V, 4);
-    fr::LaunchTimer _lt("dcor_bwd_kernel", st);
-    if (d == 64) dcor_bwd_kernel<64><<<g, kThreads, 0, st>>>(vw, pr, idx, n, Dm, rowmean, gm, dfds, g_out);
-    else if (d == 32) dcor_bwd_kernel<32><<<g, kThreads, 0, st>>>(vw, pr, idx, n, Dm, rowmean, gm, dfds, g_out);
+    float *W = ws, *wsum = ws + (size_t)kMaxV * n * n;
+    {
+        fr::LaunchTimer _lt("dcor_w_kernel", st);
+        dcor_w_kernel<<<(n + kRB2 - 1) / kRB2, kThreads, 0, st>>>(V, pr, n, Dm, rowmean, gm, dfds, g_out, W, wsum);
+        if (int rc = fr::check_launch("fr_dcor_bwd/w")) return rc;
+    }
+    dim3 g((n + 31) / 32, V, 8);
+    fr::LaunchTimer _lt("dcor_wx_kernel", st);
+    if (d == 64) dcor_wx_kernel<64><<<g, kThreads, 0, st>>>(vw, idx, n, W, wsum);
+    else if (d == 32) dcor_wx_kernel<32><<<g, kThreads, 0, st>>>(vw, idx, n, W, wsum);
     else {
         fr::set_error("fr_dcor_bwd: d=%d unsupported (32, 64)", d);
         return FR_EUNSUPPORTED;

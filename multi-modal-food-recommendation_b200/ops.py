@@ -546,9 +546,10 @@ def _dcor_backward(tabs, idx, pairs, state, g_terms, d_tabs, masks=None):
     Dm, rowmean, dfds, gm = state
     V, P, n, d = len(tabs), len(pairs), idx.numel(), tabs[0].shape[1]
     pr = (C.c_int32 * (2 * P))(*[x for ab in pairs for x in ab])
+    ws = torch.empty(int(_L.fr_dcor_bwd_ws_floats(n)), dtype=torch.float32, device=idx.device)   # W matrices + row sums
     _lib.check(_L.fr_dcor_bwd(_ptr_array(tabs), V, d, idx.data_ptr(), n, pr, P, Dm.data_ptr(), rowmean.data_ptr(),
                               dfds.data_ptr(), gm.data_ptr(), g_terms.data_ptr(), _ptr_array(d_tabs),
-                              _ptr_array(masks) if masks is not None else None, _lib.stream_ptr()), "fr_dcor_bwd")
+                              _ptr_array(masks) if masks is not None else None, ws.data_ptr(), _lib.stream_ptr()), "fr_dcor_bwd")
 
 
 def _term_grads(g_terms, g_total, P):

@@ -12,6 +12,7 @@ def main():
     mask = (sys.argv[1] if len(sys.argv) > 1 else "nomask") == "mask"
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     M = int(sys.argv[3]) if len(sys.argv) > 3 else 148 * 128 * 4
+    H = int(sys.argv[4]) if len(sys.argv) > 4 else 20
     N, K = 500_000, 64
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(4)
@@ -20,12 +21,12 @@ def main():
     Ub, Ib = E.to_bf16(U), E.to_bf16(I)
     kw = {}
     if mask:
-        hidx = torch.sort(torch.randint(0, N, (M, 20), device=dev, generator=g), dim=1)[0].to(torch.int32).reshape(-1)
+        hidx = torch.sort(torch.randint(0, N, (M, max(H, 1)), device=dev, generator=g), dim=1)[0].to(torch.int32).reshape(-1)
 
-        class H:
-            ptr = torch.arange(0, 20 * M + 1, 20, device=dev, dtype=torch.int64)
+        class Hist:
+            ptr = torch.arange(0, H * M + 1, max(H, 1), device=dev, dtype=torch.int64) if H > 0 else torch.zeros(M + 1, device=dev, dtype=torch.int64)
             idx = hidx
-        kw = dict(row_ids=torch.arange(M, device=dev), hist=H)
+        kw = dict(row_ids=torch.arange(M, device=dev), hist=Hist)
     fn = lambda: E.gemm_topk(U, I, k, exact=False, A_bf16=Ub, B_bf16=Ib, **kw)
     fn(); torch.cuda.synchronize()
     ts = []
@@ -35,7 +36,7 @@ def main():
         ts.append(a.elapsed_time(b))
     t = min(ts)
     env = {k_: v for k_, v in os.environ.items() if k_.startswith("FR_TOPK")}
-    print(json.dumps({"env": env, "mask": mask, "k": k, "M": M, "ms": round(t, 3), "tflops": round(2.0 * M * N * K / t / 1e9, 1),
+    print(json.dumps({"env": env, "mask": mask, "hist_len": H if mask else None, "k": k, "M": M, "ms": round(t, 3), "tflops": round(2.0 * M * N * K / t / 1e9, 1),
                       "frac_burst": round(2.0 * M * N * K / t / 1e9 / 1645.6, 4)}))
 
 

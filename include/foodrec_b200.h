@@ -150,6 +150,14 @@ int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, const int64_
                      const float *gnorm, float *const *d_tab_host, uint8_t *emb_mask /* [n_rows] zeroed, or NULL */,
                      void *stream);
 
+/* The two loss modules in their stand-alone form, for callers that already hold scores / gathered rows
+ * (`self.mf_loss(pos_scores, neg_scores)`, `self.reg_loss(u_ego, pos_ego, neg_ego)`: FoodRec/common/loss.py:31-34, 44-50).
+ *   fr_bpr_scores_fwd: out[0] = -(1/n) sum_i log(gamma + sigmoid(pos[i] - neg[i])); coef[i] = d out / d pos[i] = -d out / d neg[i].
+ *   fr_l2_norm_f32:    out[0] = sqrt(sum_i x[i]^2) (torch.norm(x, p=2) of the flattened tensor).
+ * One block each, fixed summation order (bit-reproducible); meant for batch-sized inputs. */
+int fr_bpr_scores_fwd(const float *pos, const float *neg, int64_t n, float gamma, float *out, float *coef, void *stream);
+int fr_l2_norm_f32(const float *x, int64_t n, float *out, void *stream);
+
 /* Row pointers of a CSR from the row indices of a COO (any order; for a row-major-sorted COO -- what the
  * reference builds, FoodRec/models/cikm_model.py:174-180 -- `col`/`val` are then already in CSR order).
  * row_ptr: int32[n_rows + 1]; scratch: int32[n_rows]. */

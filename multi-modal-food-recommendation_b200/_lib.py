@@ -46,6 +46,8 @@ SIGNATURES = {
     "fr_rank_loss_ws_floats": (_i64, []),
     "fr_rank_loss_fwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _f32, _i32, _p, _p, _p, _f32, _p, _p, _p, _p, _p]),
     "fr_rank_loss_bwd": (C.c_int, [_p, _i32, _i64, _p, _p, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _p]),
+    "fr_bpr_scores_fwd": (C.c_int, [_p, _p, _i64, _f32, _p, _p, _p]),
+    "fr_l2_norm_f32": (C.c_int, [_p, _i64, _p, _p]),
     "fr_spmm_csr_f32_masked": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i32, _p, _p, _f32, _f32, _p, _p, _p, _p, _p, _p]),
     "fr_dcor_ws_floats": (_i64, [_i32]),
     "fr_dcor_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _i32, _f32, _p, _p, _p, _p, _p, _p, _p]),

@@ -143,6 +143,42 @@ rank_loss_bwd_kernel(const float *__restrict__ emb, int d, long long item_off, c
     }
 }
 
+// Stand-alone forms of the two loss modules (FoodRec/common/loss.py:31-34, 44-50) for callers that already hold
+// scores / gathered rows (batch-sized inputs): ONE block, fixed summation order, so the value is bit-reproducible.
+__global__ void __launch_bounds__(1024)
+bpr_scores_kernel(const float *__restrict__ pos, const float *__restrict__ neg, long long n, float gamma,
+                  float *__restrict__ out, float *__restrict__ coef) {
+    __shared__ float sh[32];
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = pos[i] - neg[i];
+        const float sg = 1.f / (1.f + expf(-x));
+        s += -logf(gamma + sg);
+        coef[i] = -(sg * (1.f - sg)) / ((gamma + sg) * (float)n);   // d out / d pos[i] = -d out / d neg[i]
+    }
+    s = fr::warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = fr::warp_sum(threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f);
+        if (threadIdx.x == 0) out[0] = s / (float)n;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+l2_norm_kernel(const float *__restrict__ x, long long n, float *__restrict__ out) {
+    __shared__ float sh[32];
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(x[i], x[i], s);
+    s = fr::warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = fr::warp_sum(threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f);
+        if (threadIdx.x == 0) out[0] = sqrtf(s);
+    }
+}
+
 int fill_groups(Groups &g, int n_groups, const float *const *tab, const int64_t *const *idx, const int64_t *cnt,
                 const int64_t *pad, float *const *dtab) {
     FR_REQUIRE(n_groups >= 0 && n_groups <= FR_MAX_REG_GROUPS, "rank_loss: n_groups=%d out of range", n_groups);
@@ -202,4 +238,21 @@ extern "C" int fr_rank_loss_bwd(const float *emb, int32_t d, int64_t item_off, c
     rank_loss_bwd_kernel<<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(emb, d, item_off, u, p, n, B, coef, g_out,
                                                                          d_emb, g, reg_den, gnorm, emb_mask);
     return fr::check_launch("fr_rank_loss_bwd");
+}
+
+extern "C" int fr_bpr_scores_fwd(const float *pos, const float *neg, int64_t n, float gamma, float *out, float *coef,
+                                 void *stream) {
+    FR_REQUIRE(pos && neg && out && coef, "fr_bpr_scores_fwd: null pointer");
+    FR_REQUIRE(n > 0, "fr_bpr_scores_fwd: n=%lld", (long long)n);
+    fr::LaunchTimer _lt("bpr_scores_kernel", (cudaStream_t)stream);
+    bpr_scores_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pos, neg, n, gamma, out, coef);
+    return fr::check_launch("fr_bpr_scores_fwd");
+}
+
+extern "C" int fr_l2_norm_f32(const float *x, int64_t n, float *out, void *stream) {
+    FR_REQUIRE(x && out, "fr_l2_norm_f32: null pointer");
+    FR_REQUIRE(n > 0, "fr_l2_norm_f32: n=%lld", (long long)n);
+    fr::LaunchTimer _lt("l2_norm_kernel", (cudaStream_t)stream);
+    l2_norm_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out);
+    return fr::check_launch("fr_l2_norm_f32");
 }

@@ -56,6 +56,34 @@ def test_bpr_and_embloss_golden():
     close(reg, g["emb/out"][0])
 
 
+def test_loss_modules_called_directly_match_reference_golden():
+    """`model.mf_loss(pos, neg)` / `model.reg_loss(e1, e2, e3)` as reference code calls them (FoodRec/common/loss.py:31-34,
+    44-50): values against the reference-run golden, gradients against the same formula in torch-CPU."""
+    from foodrec_b200.common.loss import BPRLoss, EmbLoss
+    g = load_golden("primitives.npz")
+    pos, neg = torch.from_numpy(g["bpr/pos"]), torch.from_numpy(g["bpr/neg"])
+    pd, nd = pos.cuda().requires_grad_(True), neg.cuda().requires_grad_(True)
+    out = BPRLoss()(pd, nd)
+    close(out, g["bpr/out"])
+    out.backward()
+    pc, nc = pos.clone().requires_grad_(True), neg.clone().requires_grad_(True)
+    (-torch.log(1e-10 + torch.sigmoid(pc - nc)).mean()).backward()
+    close(pd.grad, pc.grad.numpy(), rtol=2e-5)
+    close(nd.grad, nc.grad.numpy(), rtol=2e-5)
+    es = [torch.from_numpy(g[k]) for k in ("emb/e1", "emb/e2", "emb/e3")]
+    ed = [e.cuda().requires_grad_(True) for e in es]
+    reg = EmbLoss()(*ed)
+    assert tuple(reg.shape) == (1,)
+    close(reg, g["emb/out"])
+    (reg.sum() * 1.7).backward()
+    ec = [e.clone().requires_grad_(True) for e in es]
+    (sum(torch.norm(e, p=2) for e in ec) / ec[-1].shape[0] * 1.7).backward()
+    for a, b in zip(ed, ec):
+        close(a.grad, b.grad.numpy(), rtol=2e-5)
+    with pytest.raises(Exception):
+        BPRLoss()(pos, neg)          # CPU tensors: no fallback
+
+
 def test_distance_correlation_golden_and_grad():
     """Against the reference golden (fp32, CPU) and against the same formula evaluated in fp64.
 

@@ -15,7 +15,7 @@ build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/foodrec_b200.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 
 $(LIB): $(OBJS)
-	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -lcudart
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -lcudart -ldl
 
 clean:
 	rm -rf build $(LIB)

@@ -865,10 +865,14 @@ def _bench_partitioned_propagation(dev, rank, world, barrier, peaks):
     nnz_local = pg.local.nnz
     del g
     el = pg.local_rows(ego).requires_grad_(True)
+    try:      # the exchange through this library's C ABI (fr_allgather_rows on its own NCCL communicator)
+        comm, exchange_api = D.RowComm(device=dev), "fr_allgather_rows (C ABI, own NCCL communicator)"
+    except Exception as e:  # noqa: BLE001  (NCCL could not be bound: the same collective through torch.distributed)
+        comm, exchange_api = None, f"torch.distributed all_gather_into_tensor (fr_comm_init failed: {e})"
 
     def step_gather():
         el.grad = None
-        o = D.propagate_mean_partitioned(pg, el, layers)
+        o = D.propagate_mean_partitioned(pg, el, layers, group=comm)
         o.backward(o)
     for _ in range(2):
         step_gather()
@@ -884,7 +888,7 @@ def _bench_partitioned_propagation(dev, rank, world, barrier, peaks):
     xf = torch.randn(pg.n_padded, d, device=dev)
     yl = torch.empty(pg.rows_per_rank, d, device=dev)
     k_ms = timed_ms(lambda: ops.spmm(pg.local, xf, Z=el.detach(), alpha=0.5, beta=0.5, out=yl), 10, warm=2)
-    ag_ms = timed_ms(lambda: D._all_gather_rows(el.detach()), 10, warm=2)
+    ag_ms = timed_ms(lambda: D._all_gather_rows(el.detach(), comm), 10, warm=2)
     t_push, push_err = None, None
     try:
         tables = D.PeerTables(pg.n_padded, d, dev)
@@ -911,10 +915,12 @@ def _bench_partitioned_propagation(dev, rank, world, barrier, peaks):
         push_err = f"push path unavailable: {e}"
     t = torch.tensor([t_gather, k_ms, ag_ms, t_push if t_push is not None else 0.0], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if comm is not None:
+        comm.close()
     recv = (world - 1) * pg.rows_per_rank * d * 4
     nb_local = 8 * nnz_local + 4 * (pg.rows_per_rank + 1) + 4 * d * pg.n_padded + 4 * d * pg.rows_per_rank
     out.update(
-        all_gather={"ms_fwd_bwd_max_over_ranks": float(t[0]), "exchanges": 2 * layers,
+        all_gather={"ms_fwd_bwd_max_over_ranks": float(t[0]), "exchanges": 2 * layers, "api": exchange_api,
                     "one_all_gather_ms": float(t[2]), "bytes_received_per_rank_per_layer": recv,
                     "all_gather_GBs_per_rank": recv / (float(t[2]) * 1e-3) / 1e9,
                     "nvlink_frac_of_770GBs": recv / (float(t[2]) * 1e-3) / 1e9 / 770.0},

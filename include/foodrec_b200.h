@@ -51,10 +51,14 @@ int fr_profile_dump(char *buf, int64_t cap);
  * serialise a warp; rows longer than a segment are reduced deterministically (fixed order) by the
  * last segment to finish.  The segment plan is built once per graph:
  *
- *   fr_spmm_plan_sizes : from `row_ptr_host` compute n_seg, n_long (rows split in >1 segment),
- *                        n_part (total segments belonging to long rows).
+ *   fr_spmm_plan_sizes : from `row_ptr_host` compute n_seg, n_long (fold entries of the rows split in >1 segment),
+ *                        n_part (partial-row slots of the fold workspace).
  *   fr_spmm_plan_fill  : fill host arrays seg[n_seg*4] (row, start, len, long_id|-1),
- *                        long_rows[n_long*4] (first_seg, n_parts, part_base, row).
+ *                        long_rows[n_long*4] (first_seg, n_parts, part_base, row).  A row of more than 16 segments folds
+ *                        in two levels: ~sqrt(k) child entries (first_seg, n_parts, part_base, -(parent + 1)), contiguous
+ *                        and directly followed by their parent entry (first_child, n_children, part_base, row), so the
+ *                        serial chain of the last arriver is ~2 sqrt(k) loads instead of k.  The shape depends on the
+ *                        row's length only.
  *   The caller uploads both, and provides `partial` (n_part * d floats) and `counters` (n_long int32,
  *   zero-initialised once; the kernel leaves them zero).
  *
@@ -304,6 +308,21 @@ int fr_schgn_score(const float *user_final, const float *user_hidden, int32_t nu
  *   fr_peer_alloc   cudaMalloc (zeroed) + 64-byte IPC handle to send to the other ranks
  *   fr_peer_open    map another rank's table from its handle;  fr_peer_close / fr_peer_free  undo the two
  *   fr_push_rows    the same exchange for rows no SpMM produced (the layer-0 input) */
+/* The exchange as NCCL collectives behind this ABI (`fr_allgather_rows`).  NCCL is bound at run time
+ * (dlopen of the libnccl.so.2 the process has loaded -- PyTorch links it; FR_NCCL_LIBRARY overrides), so the library has no
+ * link-time NCCL dependency.  One communicator per process (= per GPU), created from a 128-byte unique id that rank 0
+ * obtains and the caller distributes (dist.RowComm sends it through torch.distributed):
+ *   fr_comm_unique_id       rank 0: ncclGetUniqueId -> id128
+ *   fr_comm_init            every rank, on its current device: ncclCommInitRank -> *comm;  fr_comm_destroy undoes it
+ *   fr_allgather_rows       x_full[world * rows_per_rank, d] <- every rank's x_local[rows_per_rank, d], on `stream`
+ *   fr_reduce_scatter_rows  g_local[rows_per_rank, d] <- sum over ranks of block `rank` of their g_full (the adjoint)
+ *   fr_comm_version         NCCL version code, 0 when NCCL cannot be bound */
+int fr_comm_version(void);
+int fr_comm_unique_id(void *id128);
+int fr_comm_init(const void *id128, int32_t rank, int32_t world, void **comm);
+int fr_comm_destroy(void *comm);
+int fr_allgather_rows(void *comm, const float *x_local, int64_t rows_per_rank, int32_t d, float *x_full, void *stream);
+int fr_reduce_scatter_rows(void *comm, const float *g_full, int64_t rows_per_rank, int32_t d, float *g_local, void *stream);
 int fr_peer_alloc(int64_t bytes, void **ptr, void *handle64);
 int fr_peer_open(const void *handle64, void **ptr);
 int fr_peer_close(void *ptr);

@@ -70,6 +70,12 @@ SIGNATURES = {
     "fr_gather_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
     "fr_scatter_add_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
     "fr_pair_scores": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _p, _p]),
+    "fr_comm_version": (C.c_int, []),
+    "fr_comm_unique_id": (C.c_int, [_p]),
+    "fr_comm_init": (C.c_int, [_p, _i32, _i32, _p]),
+    "fr_comm_destroy": (C.c_int, [_p]),
+    "fr_allgather_rows": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "fr_reduce_scatter_rows": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
     "fr_peer_alloc": (C.c_int, [_i64, _p, _p]),
     "fr_peer_open": (C.c_int, [_p, _p]),
     "fr_peer_close": (C.c_int, [_p]),

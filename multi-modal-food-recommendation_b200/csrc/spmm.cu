@@ -160,41 +160,56 @@ spmm_group_body(const long long w, const int4 *__restrict__ seg, long long n_seg
         }
         return;
     }
-    // ---- long row: publish this segment's partial; the last segment to arrive folds all in fixed order
-    const int4 lr = __ldg(long_rows + s.w);              // first_seg, n_parts, part_base, row
-    const int part = (int)(sidx - lr.x);
+    // ---- long row: publish this segment's partial; the last one to arrive (atomic ticket) folds the entry's partials in
+    //      fixed order.  Rows of many segments fold in TWO levels (plan: child entries of ~sqrt(k) segments each, whose
+    //      folded sums become the partials of a parent entry), so the serial chain of the last arriver is ~2 sqrt(k)
+    //      loads instead of k: the tail of the launch no longer waits for one group walking thousands of partial rows.
+    int id = s.w;
+    int4 lr = __ldg(long_rows + id);                     // first_seg | first_child, n_parts, part_base, row | -(parent + 1)
+    int slot = (int)(sidx - lr.x);
+    for (;;) {
 #pragma unroll
-    for (int t = 0; t < VPL; ++t)
-        __stcg(reinterpret_cast<float4 *>(partial + ((size_t)lr.z + part) * D + 4 * (lg + LPR * t)), acc[t]);
-    __threadfence();
-    __syncwarp(gmask);
-    int ticket = 0;
-    if (lg == 0) ticket = atomicAdd(counters + s.w, 1);
-    ticket = __shfl_sync(gmask, ticket, g * LPR);
-    if (ticket != lr.y - 1) return;
-    __threadfence();
+        for (int t = 0; t < VPL; ++t)
+            __stcg(reinterpret_cast<float4 *>(partial + ((size_t)lr.z + slot) * D + 4 * (lg + LPR * t)), acc[t]);
+        __threadfence();
+        __syncwarp(gmask);
+        int ticket = 0;
+        if (lg == 0) ticket = atomicAdd(counters + id, 1);
+        ticket = __shfl_sync(gmask, ticket, g * LPR);
+        if (ticket != lr.y - 1) return;
+        __threadfence();
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) {
+            float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float *pp = partial + (size_t)lr.z * D + 4 * (lg + LPR * t);
+            int k = 0;
+            for (; k + 8 <= lr.y; k += 8) {      // eight partial rows in flight; the fold order stays k = 0, 1, 2, ...
+                float4 p8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) p8[u] = fr::ldcg_f4(pp + (size_t)(k + u) * D);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) fr::add4(tot, p8[u]);
+            }
+            for (; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(pp + (size_t)k * D));
+            acc[t] = tot;
+        }
+        if (lg == 0) counters[id] = 0;
+        if (lr.w >= 0) break;                            // a row's own (top-level) entry: finish below
+        const int parent = -lr.w - 1;                    // child entry: its sum is partial `id - first_child` of the parent
+        const int4 pr = __ldg(long_rows + parent);
+        slot = id - pr.x;
+        id = parent;
+        lr = pr;
+    }
     bool nz_long = false;
 #pragma unroll
-    for (int t = 0; t < VPL; ++t) {
-        float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float *pp = partial + (size_t)lr.z * D + 4 * (lg + LPR * t);
-        int k = 0;
-        for (; k + 8 <= lr.y; k += 8) {          // eight partial rows in flight; the fold order stays k = 0, 1, 2, ...
-            float4 p8[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) p8[u] = fr::ldcg_f4(pp + (size_t)(k + u) * D);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) fr::add4(tot, p8[u]);
-        }
-        for (; k < lr.y; ++k) fr::add4(tot, fr::ldcg_f4(pp + (size_t)k * D));
-        nz_long |= epilogue_store<D, ACT, PUSH>(tot, lr.w, 4 * (lg + LPR * t),
+    for (int t = 0; t < VPL; ++t)
+        nz_long |= epilogue_store<D, ACT, PUSH>(acc[t], lr.w, 4 * (lg + LPR * t),
                                                 (Z != nullptr && lr.w >= sp.z_split) ? sp.Z1_adj : Z, alpha, beta, bias, Y, &sp);
-    }
     if (sp.y_mask != nullptr) {
         nz_long = __any_sync(gmask, nz_long);
         if (lg == 0) sp.y_mask[lr.w] = nz_long ? 1 : 0;
     }
-    if (lg == 0) counters[s.w] = 0;
 }
 
 template <int D, int LPR, int U, int ACT, bool SPLIT, bool MASKED, bool PUSH = false>
@@ -295,6 +310,20 @@ struct PlanCounts {
     int64_t n_seg = 0, n_long = 0, n_part = 0;
 };
 
+// Fold shape of a row of k > 1 segments: up to kFlatFold segments fold in one level (one entry); beyond that the segments
+// are dealt to `children` child entries of `per` consecutive segments (per ~ sqrt(k)) and a parent entry folds the
+// children's sums.  The shape depends on k only, so a row folds in the same order in every graph that contains it.
+constexpr int64_t kFlatFold = 16;
+struct FoldShape {
+    int64_t per, children;      // children == 0: single level
+};
+FoldShape fold_shape(int64_t k) {
+    if (k <= kFlatFold) return {k, 0};
+    int64_t per = 1;
+    while (per * per < k) ++per;
+    return {per, (k + per - 1) / per};
+}
+
 PlanCounts count_plan(const int32_t *rp, int32_t n_rows, int64_t SEG) {
     PlanCounts c;
     for (int32_t r = 0; r < n_rows; ++r) {
@@ -302,8 +331,9 @@ PlanCounts count_plan(const int32_t *rp, int32_t n_rows, int64_t SEG) {
         const int64_t k = deg <= SEG ? 1 : (deg + SEG - 1) / SEG;
         c.n_seg += k;
         if (k > 1) {
-            c.n_long += 1;
-            c.n_part += k;
+            const FoldShape f = fold_shape(k);
+            c.n_long += f.children ? f.children + 1 : 1;
+            c.n_part += k + f.children;
         }
     }
     return c;
@@ -318,6 +348,8 @@ extern "C" int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, i
     for (int32_t r = 0; r < n_rows; ++r)
         FR_REQUIRE(row_ptr_host[r + 1] >= row_ptr_host[r], "fr_spmm_plan_sizes: row_ptr not monotone at %d", r);
     const PlanCounts c = count_plan(row_ptr_host, n_rows, seg_len);
+    FR_REQUIRE(c.n_long <= 0x7fffffffLL && c.n_part <= 0x7fffffffLL && c.n_seg <= 0x7fffffffLL,
+               "fr_spmm_plan_sizes: plan too large for 32-bit ids");
     *n_seg = c.n_seg;
     *n_long = c.n_long;
     *n_part = c.n_part;
@@ -327,6 +359,8 @@ extern "C" int fr_spmm_plan_sizes(const int32_t *row_ptr_host, int32_t n_rows, i
 // Segment order: every long-row segment first (they are the critical path: the last one also
 // performs the reduction), then whole-row segments by descending length (longest-first keeps the
 // tail of the launch short); ties keep row order so neighbouring rows stay neighbours.
+// long_rows entries (int4): a row's own entry (first_seg | first_child, n_parts, part_base, row >= 0); a child entry of a
+// two-level row (first_seg, n_parts, part_base, -(parent + 1)), children contiguous and directly followed by their parent.
 extern "C" int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, int32_t seg_len, int32_t *seg_host,
                                  int32_t *long_rows_host) {
     FR_REQUIRE(row_ptr_host && seg_host && n_rows >= 0, "fr_spmm_plan_fill: bad argument");
@@ -339,20 +373,34 @@ extern "C" int fr_spmm_plan_fill(const int32_t *row_ptr_host, int32_t n_rows, in
         if (deg <= SEG) continue;
         FR_REQUIRE(long_rows_host, "fr_spmm_plan_fill: long_rows_host is null but row %d is long", r);
         const int64_t k = (deg + SEG - 1) / SEG;
-        int32_t *lr = long_rows_host + 4 * nl;
-        lr[0] = (int32_t)s;
-        lr[1] = (int32_t)k;
-        lr[2] = (int32_t)pb;
-        lr[3] = r;
-        for (int64_t i = 0; i < k; ++i, ++s) {
-            int32_t *q = seg_host + 4 * s;
-            q[0] = r;
-            q[1] = rp[r] + (int32_t)(i * SEG);
-            q[2] = (int32_t)std::min<int64_t>(SEG, deg - i * SEG);
-            q[3] = (int32_t)nl;
+        const FoldShape f = fold_shape(k);
+        const int64_t entries = f.children ? f.children : 1;
+        const int64_t parent = nl + entries;             // id of the parent entry (two-level rows only)
+        for (int64_t c = 0; c < entries; ++c) {
+            const int64_t first = c * f.per, cnt = std::min<int64_t>(f.per, k - first);
+            int32_t *lr = long_rows_host + 4 * (nl + c);
+            lr[0] = (int32_t)s;
+            lr[1] = (int32_t)cnt;
+            lr[2] = (int32_t)pb;
+            lr[3] = f.children ? (int32_t)(-(parent + 1)) : r;
+            for (int64_t i = first; i < first + cnt; ++i, ++s) {
+                int32_t *q = seg_host + 4 * s;
+                q[0] = r;
+                q[1] = rp[r] + (int32_t)(i * SEG);
+                q[2] = (int32_t)std::min<int64_t>(SEG, deg - i * SEG);
+                q[3] = (int32_t)(nl + c);
+            }
+            pb += cnt;
         }
-        pb += k;
-        ++nl;
+        if (f.children) {
+            int32_t *lr = long_rows_host + 4 * parent;
+            lr[0] = (int32_t)nl;                         // first child entry
+            lr[1] = (int32_t)f.children;
+            lr[2] = (int32_t)pb;
+            lr[3] = r;
+            pb += f.children;
+        }
+        nl += entries + (f.children ? 1 : 0);
     }
     // counting sort of the remaining rows by descending degree
     std::vector<int64_t> start((size_t)SEG + 2, 0);

@@ -1,6 +1,7 @@
 """Multi-GPU: row-partitioned propagation (one all-gather per layer) and user-sharded evaluation.
 
-One process per GPU, `torch.distributed` (NCCL over NVLink) for the plumbing.  The reference is a
+One process per GPU, `torch.distributed` (NCCL over NVLink) for the plumbing; the per-layer exchange itself is also
+available behind the C ABI (`RowComm`: `fr_allgather_rows` / `fr_reduce_scatter_rows` on this library's own communicator).  The reference is a
 single-process, single-GPU program, so there is no reference behaviour to match
 here: correctness is "N ranks reproduce the 1-rank result" (tests/test_dist_cpu.py, gloo).
 
@@ -103,7 +104,64 @@ class RowPartitionedGraph:
         return gathered.view(P, R, -1).transpose(0, 1).reshape(P * R, -1)[:self.n_nodes]
 
 
+class RowComm:
+    """This library's own NCCL communicator for the row-block collectives of the partitioned propagation
+    (`fr_comm_init`, `fr_allgather_rows`, `fr_reduce_scatter_rows`: the C-ABI form of the one exchange per layer, SURVEY.md
+    8b / 8e).  Built from the ranks of a `torch.distributed` group -- rank 0's 128-byte NCCL unique id travels through
+    that group once -- or stand-alone for a single process (`world == 1`).  Pass it wherever this module takes `group`."""
+
+    def __init__(self, group=None, device=None):
+        import ctypes as C
+        from . import _lib
+        self._lib = _lib
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise _lib.FoodRecError("RowComm needs a CUDA device (NCCL); CPU groups use torch.distributed (gloo) directly")
+        uid = C.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(_lib.lib.fr_comm_unique_id(uid), "fr_comm_unique_id")
+        if self.world > 1:
+            box = [uid.raw]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            uid = C.create_string_buffer(box[0], 128)
+        comm = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.fr_comm_init(uid, self.rank, self.world, C.byref(comm)), "fr_comm_init")
+        self._comm = comm
+
+    def all_gather_rows(self, x_local: torch.Tensor) -> torch.Tensor:
+        x_local = x_local.contiguous()
+        if not (x_local.is_cuda and x_local.dtype == torch.float32 and x_local.dim() == 2):
+            raise self._lib.FoodRecError("RowComm.all_gather_rows: expected a CUDA float32 [rows, d] block")
+        full = torch.empty((x_local.shape[0] * self.world, x_local.shape[1]), dtype=torch.float32, device=x_local.device)
+        self._lib.check(self._lib.lib.fr_allgather_rows(self._comm, x_local.data_ptr(), x_local.shape[0], x_local.shape[1],
+                                                        full.data_ptr(), self._lib.stream_ptr()), "fr_allgather_rows")
+        return full
+
+    def reduce_scatter_rows(self, g_full: torch.Tensor) -> torch.Tensor:
+        g_full = g_full.contiguous()
+        rows = g_full.shape[0] // self.world
+        if not (g_full.is_cuda and g_full.dtype == torch.float32 and g_full.dim() == 2 and rows * self.world == g_full.shape[0]):
+            raise self._lib.FoodRecError("RowComm.reduce_scatter_rows: expected a CUDA float32 [world * rows, d] table")
+        out = torch.empty((rows, g_full.shape[1]), dtype=torch.float32, device=g_full.device)
+        self._lib.check(self._lib.lib.fr_reduce_scatter_rows(self._comm, g_full.data_ptr(), rows, g_full.shape[1],
+                                                             out.data_ptr(), self._lib.stream_ptr()), "fr_reduce_scatter_rows")
+        return out
+
+    def close(self):
+        if self._comm is not None and self._comm.value:
+            torch.cuda.synchronize(self.device)
+            self._lib.check(self._lib.lib.fr_comm_destroy(self._comm), "fr_comm_destroy")
+        self._comm = None
+
+
 def _all_gather_rows(x_local: torch.Tensor, group=None) -> torch.Tensor:
+    if isinstance(group, RowComm):
+        return group.all_gather_rows(x_local)
     world = dist.get_world_size(group)
     full = torch.empty((x_local.shape[0] * world, x_local.shape[1]), dtype=x_local.dtype, device=x_local.device)
     dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
@@ -159,6 +217,8 @@ class _GatherRowsAutograd(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_full):
         g_full = g_full.contiguous()
+        if isinstance(ctx.group, RowComm):
+            return ctx.group.reduce_scatter_rows(g_full), None
         out = torch.empty((ctx.rows, g_full.shape[1]), dtype=g_full.dtype, device=g_full.device)
         if dist.get_backend(ctx.group) == "gloo":          # gloo has no reduce-scatter: all-reduce and slice
             dist.all_reduce(g_full, group=ctx.group)

@@ -37,6 +37,14 @@ def main():
     ok = torch.tensor([float(err_f < 1e-6 and err_b < 1e-6)], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 
+    # the same exchange through this library's C ABI (fr_allgather_rows / fr_reduce_scatter_rows on its own communicator)
+    comm = D.RowComm(device=dev)
+    ec = pg.local_rows(ego).requires_grad_(True)
+    outc = D.propagate_mean_partitioned(pg, ec, layers, group=comm)
+    (outc * pg.local_rows(w)).sum().backward()
+    abi_same = torch.tensor([float(torch.equal(outc, out) and torch.equal(ec.grad, el.grad))], device=dev)
+    dist.all_reduce(abi_same, op=dist.ReduceOp.MIN)
+
     # the same propagation with the exchange fused into the kernel's epilogue (peer memory, no all-gather)
     tables = D.PeerTables(pg.n_padded, 64, dev)
     ep = pg.local_rows(ego).requires_grad_(True)
@@ -67,7 +75,12 @@ def main():
         ep.grad = None
         o = D.propagate_mean_pushed(pg, ep, layers, tables)
         (o * o).sum().backward()
-    t_gather, t_push = timed(step), timed(step_push)
+
+    def step_abi():
+        ec.grad = None
+        o = D.propagate_mean_partitioned(pg, ec, layers, group=comm)
+        (o * o).sum().backward()
+    t_gather, t_push, t_abi = timed(step), timed(step_push), timed(step_abi)
 
     # row-partitioned data-parallel training step (per-rank mini-batches, all-gather forward / reduce-scatter
     # backward around the fused BPR + EmbLoss kernel) against the same step computed on one GPU
@@ -75,7 +88,7 @@ def main():
     hb = sample_train_batches(ds, 512, world, seed=4)
     batches = [{k: torch.from_numpy(b[k]).to(dev) for k in ("u_id", "pos_i_id", "neg_i_id")} for b in hb]
     pe = pg.local_rows(ego).requires_grad_(True)
-    losses = D.partitioned_bpr_losses(pg, pe, ds.n_users, layers, batches[rank], 0.1)
+    losses = D.partitioned_bpr_losses(pg, pe, ds.n_users, layers, batches[rank], 0.1, group=comm)   # C-ABI collectives
     (sum(losses) / world).backward()
     e2 = ego.clone().requires_grad_(True)
     full = ops.propagate_mean(g, e2, layers)
@@ -105,9 +118,12 @@ def main():
                           "fwd_bwd_ms_max_over_ranks": t_gather,
                           "push_bit_identical_to_all_gather_path": bool(push_same.item()),
                           "push_fwd_bwd_ms_max_over_ranks": t_push,
+                          "c_abi_collectives_bit_identical_to_torch_distributed": bool(abi_same.item()),
+                          "c_abi_fwd_bwd_ms_max_over_ranks": t_abi,
                           "partitioned_train_step": {"loss_rel_err": err_l, "grad_rel_err": err_g,
                                                      "all_ranks_ok": bool(train_ok.item()), "ms_max_over_ranks": t_train}}))
     tables.close()
+    comm.close()
     dist.destroy_process_group()
 
 

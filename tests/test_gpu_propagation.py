@@ -32,7 +32,7 @@ def to_torch_sparse(rp, col, val, n_rows, n_cols):
 
 
 @pytest.mark.parametrize("d", [32, 64, 128])
-@pytest.mark.parametrize("case", ["ragged", "long", "empty", "single"])
+@pytest.mark.parametrize("case", ["ragged", "long", "huge", "empty", "single"])
 def test_spmm_matches_sparse_mm(d, case):
     from foodrec_b200 import graph as G, ops
     rng = np.random.default_rng(1)
@@ -41,6 +41,8 @@ def test_spmm_matches_sparse_mm(d, case):
         degs = rng.integers(0, 40, size=2000)
     elif case == "long":  # rows far beyond one segment, incl. exact multiples of the segment length
         degs = np.array([5000, 128, 129, 256, 0, 1, 2999, 127, 640] + list(rng.integers(0, 300, size=300)))
+    elif case == "huge":  # thousands of segments per row: the two-level fold (children of ~sqrt(k) segments + a parent)
+        degs = np.array([300000, 3, 70000, 64 * 16, 64 * 16 + 1, 64 * 17] + list(rng.integers(0, 90, size=200)))
     elif case == "empty":
         degs = np.zeros(257, dtype=np.int64)
     else:
@@ -226,6 +228,35 @@ def test_push_epilogue_single_rank_matches_plain_propagation(mini_ds):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_row_collectives_through_the_c_abi_single_rank(mini_ds):
+    """`fr_comm_*` / `fr_allgather_rows` / `fr_reduce_scatter_rows` (NCCL bound at run time) with a one-rank
+    communicator: the partitioned propagation that exchanges through `dist.RowComm` equals `propagate_mean` bit for bit,
+    forward and backward, and the two collectives are the identity.  Multi-rank: scripts/dist_propagation_check.py."""
+    from foodrec_b200 import _lib, dist as D, graph as G, ops
+    assert _lib.lib.fr_comm_version() >= 21000
+    comm = D.RowComm(device="cuda")
+    assert (comm.rank, comm.world) == (0, 1)
+    try:
+        x = torch.randn(37, 64, device="cuda")
+        assert torch.equal(comm.all_gather_rows(x), x)
+        assert torch.equal(comm.reduce_scatter_rows(x), x)
+        g = G.norm_adj_user_item(mini_ds.train_coo_matrix, mini_ds.n_users, mini_ds.n_items, "cuda")
+        pg = D.RowPartitionedGraph.from_graph(g, 0, 1, "cuda")
+        torch.manual_seed(5)
+        ego = torch.randn(g.n_rows, 64, device="cuda") * 0.1
+        w = torch.randn(g.n_rows, 64, device="cuda")
+        a, b = ego.clone().requires_grad_(True), ego.clone().requires_grad_(True)
+        ref = ops.propagate_mean(g, a, 2)
+        (ref * w).sum().backward()
+        got = D.propagate_mean_partitioned(pg, b, 2, group=comm)
+        (got * w).sum().backward()
+        assert torch.equal(got, ref) and torch.equal(b.grad, a.grad)
+        full = D.gather_rows_autograd(b, comm)          # all-gather whose backward is the reduce-scatter
+        assert torch.equal(full, b)
+    finally:
+        comm.close()
 
 
 def test_grouped_launch_is_bit_identical_to_separate_launches():

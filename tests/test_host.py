@@ -56,10 +56,58 @@ def test_graph_builder_bit_exact_vs_reference(mini_ds):
                  g["adj/text_norm_adj/idx"], g["adj/text_norm_adj/val"])
 
 
-@pytest.mark.parametrize("degs", [[0, 1, 128, 129, 0, 1000, 5, 256, 0], [], [0, 0], [4000]])
+def _fold_shape(k):
+    """csrc/spmm.cu::fold_shape: rows of up to 16 segments fold in one level, longer ones in ~sqrt(k) children."""
+    if k <= 16:
+        return k, 0
+    per = 1
+    while per * per < k:
+        per += 1
+    return per, -(-k // per)
+
+
+def _interpret_plan(g, rp, col, val, X):
+    """What `spmm_group_kernel` computes from the plan, restated in numpy: per-segment partial sums, then the fold
+    entries in fixed order (children into their parent's slots, parents / single-level entries into the row)."""
+    seg, lr = g.seg_host[:g.n_seg], g.long_rows_host[:g.n_long]
+    Y = np.zeros((len(rp) - 1, X.shape[1]), np.float64)
+    part = np.full((max(g.n_part, 1), X.shape[1]), np.nan)
+    arrived = np.zeros(max(g.n_long, 1), np.int64)
+    written = np.zeros(len(rp) - 1, np.int64)
+
+    def publish(entry, slot, acc):
+        first, n_parts, pbase, row = lr[entry]
+        assert 0 <= slot < n_parts and np.isnan(part[pbase + slot]).all()
+        part[pbase + slot] = acc
+        arrived[entry] += 1
+        if arrived[entry] < n_parts:
+            return
+        tot = part[pbase:pbase + n_parts].sum(0)
+        if row >= 0:
+            Y[row] = tot
+            written[row] += 1
+        else:
+            parent = -row - 1
+            publish(parent, entry - lr[parent][0], tot)
+    for i, (r, st, ln, lid) in enumerate(seg):
+        acc = (val[st:st + ln, None] * X[col[st:st + ln]]).sum(0) if ln else np.zeros(X.shape[1])
+        if lid < 0:
+            Y[r] = acc
+            written[r] += 1
+        else:
+            publish(lid, i - lr[lid][0], acc)
+    assert (written == 1).all() and (arrived == lr[:, 1]).all() if g.n_long else (written == 1).all()
+    return Y
+
+
+@pytest.mark.parametrize("degs", [[0, 1, 128, 129, 0, 1000, 5, 256, 0], [], [0, 0], [4000], [64 * 16, 64 * 16 + 1, 70000, 3, 64 * 290]])
 def test_segment_plan_covers_every_nonzero_once(degs):
     rp = np.concatenate([[0], np.cumsum(degs)]).astype(np.int32)
-    g = G.PropGraph(rp, np.zeros(rp[-1], np.int32), np.ones(rp[-1], np.float32), max(len(degs), 1), "cpu")
+    rng = np.random.default_rng(len(degs))
+    n_cols = 37
+    col = rng.integers(0, n_cols, int(rp[-1])).astype(np.int32)
+    val = rng.standard_normal(int(rp[-1])).astype(np.float32)
+    g = G.PropGraph(rp, col, val, n_cols, "cpu")
     seg = g.seg_host[:g.n_seg]
     assert g.n_seg == sum(max(1, -(-d // G.SEG)) for d in degs)
     seen = np.zeros(int(rp[-1]), dtype=np.int32)
@@ -71,13 +119,30 @@ def test_segment_plan_covers_every_nonzero_once(degs):
         assert (lid >= 0) == (degs[r] > G.SEG)
     assert (seen == 1).all() and rows_seen == set(range(len(degs)))
     lr = g.long_rows_host[:g.n_long]
-    assert g.n_long == sum(d > G.SEG for d in degs)
-    assert g.n_part == sum(-(-d // G.SEG) for d in degs if d > G.SEG)
+    ks = [-(-d // G.SEG) for d in degs if d > G.SEG]
+    assert g.n_long == sum(1 + (_fold_shape(k)[1] if _fold_shape(k)[1] else 0) for k in ks)
+    assert g.n_part == sum(k + _fold_shape(k)[1] for k in ks)
+    slots = np.zeros(max(g.n_part, 1), np.int32)
     for k, (first, nparts, pbase, row) in enumerate(lr):
-        assert (seg[first:first + nparts, 0] == row).all() and (seg[first:first + nparts, 3] == k).all()
+        slots[pbase:pbase + nparts] += 1
+        if row >= 0 and not (k > 0 and lr[k - 1][3] == -(k + 1)):          # a single-level row
+            assert (seg[first:first + nparts, 0] == row).all() and (seg[first:first + nparts, 3] == k).all()
+            assert nparts <= 16
+        elif row >= 0:                                                   # a parent: its children precede it, contiguously
+            assert first + nparts == k and (lr[first:k, 3] == -(k + 1)).all()
+        else:                                                            # a child
+            parent = -row - 1
+            assert lr[parent][3] >= 0 and lr[parent][0] <= k < parent
+            assert (seg[first:first + nparts, 0] == lr[parent][3]).all() and (seg[first:first + nparts, 3] == k).all()
+    assert (slots[:g.n_part] == 1).all()
     # whole-row segments come sorted by descending length
     single = seg[seg[:, 3] < 0][:, 2]
     assert (np.diff(single) <= 0).all()
+    # the plan, interpreted the way the kernel walks it, is the product
+    X = rng.standard_normal((n_cols, 8))
+    import scipy.sparse as sp
+    ref = sp.csr_matrix((val.astype(np.float64), col, rp), shape=(len(degs), n_cols)) @ X if len(degs) else np.zeros((0, 8))
+    np.testing.assert_allclose(_interpret_plan(g, rp, col, val.astype(np.float64), X), ref, rtol=1e-9, atol=1e-9)
 
 
 def test_gcn_normalisation_matches_oracle(mini_ds):

@@ -18,6 +18,7 @@ Beside the headline the same JSON line carries (each with its own roofline):
   partitioned_propagation row-partitioned 3-layer fwd+bwd propagation on a C5-shaped device-built graph (same total
                           problem at every N: strong scaling), NCCL all-gather path and peer-store (push) path
   knn                     cosine kNN (D = 4096 / 384) and centroid assignment shapes of the ranking kernel
+  clussl_c3               the same CLUSSL step on the Foodcom-scale synthetic C3 (BASELINE.json configs[2]), 1 and N GPUs
   torch_cuda_baseline     the stock-PyTorch-on-the-same-GPU arm (uncoalesced COO `torch.sparse.mm`, stack/mean,
                           autograd, default Adam; `matmul` + `topk`): the bar SURVEY.md 2.1 names
   cpu_baseline            the oracle port on the host cores (context only)
@@ -438,6 +439,7 @@ def main():
         extras["partitioned_propagation"] = _bench_partitioned_propagation(dev, rank, world, barrier, peaks)
         if world > 1:
             extras["dp_control"] = _bench_dp_control(model, ds, cfg, dev, world, steps_per_epoch)
+        extras["clussl_c3"] = _bench_c3(dev, rank, world, barrier)
     times = torch.tensor([ms_dev, ms_e2e, ev["ms_dev"], ev["ms_e2e"], ev["kernel_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -961,6 +963,46 @@ def _bench_dp_control(model, ds, cfg, dev, world, steps_per_epoch):
     ms = timed_ms(lambda: step(bt[next(it) % 4]), 100, warm=5)
     return {"what": f"single-GPU CLUSSL step at B = {B} (= {world} x {BATCH}) on the same C2 graph, CUDA-graph replay",
             "ms_per_step": ms, "epochs_per_s_at_global_batch": (B / BATCH) / (steps_per_epoch * ms * 1e-3)}
+
+
+def _bench_c3(dev, rank, world, barrier):
+    """BASELINE.json configs[2]: CLUSSL with k-means item graphs + the contrastive term on the Foodcom-scale synthetic C3
+    (7 600 users / 30 000 items / 192 000 interactions, 2 x 2 000 clusters), 1 and N GPUs.  Same step as the headline
+    (CUDA-graph replay; N > 1: replicated graph, per-rank batches, gradient all-reduce inside the captured step)."""
+    from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
+    from foodrec_b200.synth import make_dataset, sample_train_batches
+    from foodrec_b200.train import FusedAdam, GraphedTrainStep, OverlappedGradAllReduce
+    ds = make_dataset("C3")
+    cfg = model_cfg(ds, str(dev))
+    torch.manual_seed(999)
+    m = PRICAI_ModelX(cfg, ds).to(dev).train()
+    opt = FusedAdam(m.parameters(), lr=cfg["learning_rate"])
+    keys = ("u_id", "pos_i_id", "neg_i_id")
+    bt = [{k: torch.from_numpy(b[k]).to(dev) for k in keys} for b in sample_train_batches(ds, BATCH, 8, seed=31 + rank)]
+    hook = OverlappedGradAllReduce(m) if world > 1 else None
+    step = GraphedTrainStep(m, opt, bt[0], keys=keys, grad_hook=hook)
+    for i in range(5):
+        step(bt[i % 8])
+    barrier()
+    a, b = ev_pair()
+    a.record()
+    n = 300
+    for i in range(n):
+        step(bt[i % 8])
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    spe = math.ceil(ds.n_train / BATCH)
+    if hook is not None:
+        hook.remove()
+    return {"workload": f"C3: CLUSSL train step, B={BATCH} per rank, {ds.n_users} users / {ds.n_items} items / {ds.n_train} train "
+                        f"interactions, {ds.cfg.n_cluster} clusters x2, {ds.num_ingredients} ingredients; {world} GPU(s)",
+            "ms_per_step_max_over_ranks": ms, "steps_per_epoch": spe, "timed_steps": n,
+            "train_epochs_per_s": world / (spe * ms * 1e-3)}
 
 
 def _bench_knn(ds, dev, tpeak):

@@ -33,12 +33,6 @@
 
 #include "rank_common.cuh"
 
-namespace rk {
-int launch_topk_v2(const CUtensorMap &ma, const CUtensorMap &mb, const Params &P, void *ws, int64_t ws_bytes, int two_pass,
-                   int bstride, cudaStream_t stream);
-int64_t topk_v2_ws_bytes(int32_t M);
-}  // namespace rk
-
 namespace {
 using namespace rk;
 
@@ -836,15 +830,6 @@ int launch_pair(const CUtensorMap &ma, const CUtensorMap &mb, const PairParams &
     return fr::check_launch("fr_gemm_topk_bf16");
 }
 
-int topk_impl() {
-    static int impl = -1;
-    if (impl < 0) {
-        const char *e = getenv("FR_TOPK_IMPL");
-        impl = e ? atoi(e) : 3;
-    }
-    return impl;
-}
-
 }  // namespace
 
 extern "C" int fr_f32_to_bf16(const float *x, void *y, int64_t rows, int32_t d, int32_t l2_normalise, void *stream) {
@@ -859,8 +844,7 @@ extern "C" int fr_f32_to_bf16(const float *x, void *y, int64_t rows, int32_t d, 
 }
 
 extern "C" int64_t fr_gemm_topk_ws_bytes(int32_t M) {
-    const int64_t pair = (int64_t)plan_pair(M, 64, true).grid * BM * 4 * (CAP * 8 + OWN_CAP * 4);
-    return std::max(pair, rk::topk_v2_ws_bytes(M));
+    return (int64_t)plan_pair(M, 64, true).grid * BM * 4 * (CAP * 8 + OWN_CAP * 4);
 }
 
 extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_t N, int32_t K, float scale,
@@ -875,10 +859,9 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
     FR_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "fr_gemm_topk_bf16: operands must be 16-byte aligned");
     FR_REQUIRE((row_ids == nullptr) == (hist_ptr == nullptr) && (row_ids == nullptr) == (hist_idx == nullptr),
                "fr_gemm_topk_bf16: row_ids / hist_ptr / hist_idx go together");
-    const bool pair = topk_impl() != 2;
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, A, M, K, BM)) return rc;
-    if (int rc = make_map(&mb, B, N, K, pair ? BN / 2 : BN)) return rc;
+    if (int rc = make_map(&mb, B, N, K, BN / 2)) return rc;       // each CTA of the pair loads half of a B tile
     Params P{M, N, K, topk, scale, bias, row_ids, hist_ptr, hist_idx, out_val, out_idx};
     // The bounding sweep doubles the MMA work: worth it while the epilogue is the bottleneck (short inner
     // dimension: full-sort scoring, K = 64), not when a tile already carries many k-blocks (kNN, K = 384..4096).
@@ -894,7 +877,6 @@ extern "C" int fr_gemm_topk_bf16(const void *A, int32_t M, const void *B, int32_
     const int n_nblk_h = (int)((N + BN - 1) / BN);
     const int bstride = std::max(1, std::min(bstride_env > 0 ? bstride_env : (n_nblk_h >= 1024 ? 2 : 1), n_nblk_h / 32));
     cudaStream_t st = (cudaStream_t)stream;
-    if (!pair) return rk::launch_topk_v2(ma, mb, P, ws, ws_bytes, two_pass, bstride, st);
     const PairLaunch L = plan_pair(M, K, two_pass != 0);
     const int64_t need = (int64_t)L.grid * BM * 4 * (CAP * 8 + OWN_CAP * 4);
     FR_REQUIRE(ws != nullptr && ws_bytes >= need, "fr_gemm_topk_bf16: workspace of %lld bytes required (got %lld)",

@@ -1,4 +1,4 @@
-"""Ranking kernel microbenchmark: FR_TOPK_IMPL=3 (cluster pair, default) vs 2 (previous kernel) on the judged shapes.
+"""Ranking kernel microbenchmark (`rank_topk_pair_kernel`) on the judged shapes.
 usage: python scripts/microbench_rank.py [c4|knn|text|all]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,7 +23,7 @@ def timeit(fn, iters=3, warm=1):
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     dev = "cuda"
-    out = {"impl": os.environ.get("FR_TOPK_IMPL", "3")}
+    out = {"impl": "rank_topk_pair_kernel"}
     peak = 1645.6
     if which in ("c4", "all"):
         M, N, K, k = 148 * 128 * 4, 500_000, 64, 32

@@ -59,39 +59,55 @@ def test_clussl_matches_reference_golden(mini_ds, mini_batches):
     close(sc, g["infer/scores"])
 
 
-def test_clussl_c1_vs_oracle():
+def _oracle_clussl(ds, sd, batch, dtype):
+    """The oracle's CLUSSL forward + losses + gradients (pricai_modelx.py:179-276 restated) in `dtype` on the CPU."""
+    from oracle import adjacency, losses, propagation
+    names = ("user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight",
+             "image_prototype_embedding.weight", "text_prototype_embedding.weight")
+    P = {k: sd[k].clone().to(dtype).requires_grad_(True) for k in names}
+    S = [adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items),
+         adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients),
+         adjacency.norm_adj_item_side(ds.image_cluster_triples, ds.n_items, ds.cfg.n_cluster),
+         adjacency.norm_adj_item_side(ds.text_cluster_triples, ds.n_items, ds.cfg.n_cluster)]
+    S = [x.to(dtype) for x in S]
+    out = propagation.clussl_forward(*S, *(P[k] for k in names), ds.n_users, ds.n_items, ds.num_ingredients,
+                                     ds.cfg.n_cluster, 2, 1)
+    u, p, n = (torch.from_numpy(batch[k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+    terms = losses.clussl_loss(out, P["user_embedding.weight"], P["item_embedding.weight"], u, p, n, 0.01, 0.1)
+    sum(terms).sum().backward()
+    return out, [float(t) for t in terms], {k: v.grad for k, v in P.items()}
+
+
+@pytest.mark.parametrize("scale", ["C1", "C3"])
+def test_clussl_train_step_vs_oracle(scale):
+    """Forward tables, every loss term and every parameter gradient of one CLUSSL batch at C1 and at the Foodcom-scale
+    C3 (BASELINE.json configs[2]) against the CPU oracle.  Tables and losses: 1e-5 (north star).  Gradients: 2e-5 of the
+    fp32 oracle, or -- the distance-correlation term is ill-conditioned, the fp32 oracle itself sits up to ~1e-4 from
+    exact arithmetic -- at least as close to the fp64 oracle as the fp32 oracle is."""
     from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
     from foodrec_b200.synth import make_dataset, sample_train_batches
-    from oracle import adjacency, losses, propagation
-    ds = make_dataset("C1")
+    ds = make_dataset(scale)
     torch.manual_seed(999)
     m = PRICAI_ModelX(cfg_for(ds, train_batch_size=512), ds)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     m = m.to("cuda")
-    P = {k: sd[k].clone().requires_grad_(True) for k in (
-        "user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight",
-        "image_prototype_embedding.weight", "text_prototype_embedding.weight")}
-    S_ui = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
-    S_g = adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients)
-    S_v = adjacency.norm_adj_item_side(ds.image_cluster_triples, ds.n_items, ds.cfg.n_cluster)
-    S_t = adjacency.norm_adj_item_side(ds.text_cluster_triples, ds.n_items, ds.cfg.n_cluster)
-    out = propagation.clussl_forward(S_ui, S_g, S_v, S_t, P["user_embedding.weight"], P["item_embedding.weight"],
-                                     P["ingre_embedding.weight"], P["image_prototype_embedding.weight"],
-                                     P["text_prototype_embedding.weight"], ds.n_users, ds.n_items,
-                                     ds.num_ingredients, ds.cfg.n_cluster, 2, 1)
     batch = sample_train_batches(ds, 512, 1, seed=3)[0]
-    u, p, n = (torch.from_numpy(batch[k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
-    terms = losses.clussl_loss(out, P["user_embedding.weight"], P["item_embedding.weight"], u, p, n, 0.01, 0.1)
-    sum(terms).sum().backward()
+    out, terms, g32 = _oracle_clussl(ds, sd, batch, torch.float32)
+    _, terms64, g64 = _oracle_clussl(ds, sd, batch, torch.float64)
     got = m.calculate_loss(dev_batch(batch))
-    close(torch.stack([x.reshape(()) for x in got]), [float(t) for t in terms])
+    close(torch.stack([x.reshape(()) for x in got]), terms)
     sum(got).backward()
     ua, ia, _ = m.forward()
     close(ua, out[0].detach().numpy())
     close(ia, out[1].detach().numpy())
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max())
     for name, p_ in m.named_parameters():
-        if name in P:
-            close(p_.grad, P[name].grad.numpy(), rtol=5e-4)
+        if name in g32:
+            g = p_.grad.cpu()
+            e32, e64, o64 = rel(g, g32[name]), rel(g, g64[name]), rel(g32[name], g64[name])
+            assert e32 <= 2e-5 or e64 <= o64 + 2e-5, (name, e32, e64, o64)
 
 
 def test_grouped_item_side_launch_equals_separate_streams(mini_ds, mini_batches):

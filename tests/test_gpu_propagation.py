@@ -54,6 +54,10 @@ def test_spmm_matches_sparse_mm(d, case):
     bias = torch.randn(d)
     S = to_torch_sparse(rp, col, val, len(degs), n_cols)
     ref = torch.sparse.mm(S, X)
+    if case == "huge":
+        # a sequential fp32 sum of 300 000 terms (torch-CPU's row order) is itself 4e-6 .. 1.2e-5 away from the exact
+        # product, so the yardstick here is the fp64 product; the segmented fixed-order fold must sit well inside 1e-5
+        ref = torch.sparse.mm(S.double(), X.double()).float()
     close(ops.spmm(g, X.cuda()), ref)
     close(ops.spmm(g, X.cuda(), Z=Z.cuda(), alpha=0.25, beta=0.5), 0.25 * ref + 0.5 * Z)
     close(ops.spmm(g, X.cuda(), bias=bias.cuda(), act=1), torch.tanh(ref + bias))

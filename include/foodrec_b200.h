@@ -249,6 +249,17 @@ int fr_exact_topk_f32(const float *A, const int64_t *a_rows, int32_t Mf, const f
                       float scale, const float *bias, int32_t metric, const int64_t *hist_rows,
                       const int64_t *hist_ptr, const int32_t *hist_idx, int32_t k, float *scores_ws, float *out_val,
                       int64_t *out_idx, void *stream);
+/* The same rows with a per-row THRESHOLD: `thr[r]` is a lower bound of row r's k-th best fp32 score (the caller has it
+ * from the re-scored candidates, minus a rounding margin), so only columns scoring >= thr[r] can belong to the result.
+ * Nothing dense is written: the SIMT fp32 scoring pass appends the few qualifying (score, column) pairs to a per-row
+ * list (history columns dropped by binary search) and one CTA per row sorts its list (score desc, column asc).
+ * ws: fr_exact_topk_thr_ws_bytes(Mf) bytes, 8-byte aligned.  *overflow (device int) = rows whose list did not fit
+ * (massive ties): their outputs are untouched and the caller re-runs them with fr_exact_topk_f32. */
+int64_t fr_exact_topk_thr_ws_bytes(int32_t Mf);
+int fr_exact_topk_thr_f32(const float *A, const int64_t *a_rows, int32_t Mf, const float *B, int32_t N, int32_t d,
+                          float scale, const float *bias, int32_t metric, const int64_t *hist_rows,
+                          const int64_t *hist_ptr, const int32_t *hist_idx, int32_t k, const float *thr, void *ws,
+                          float *out_val, int64_t *out_idx, int32_t *overflow, void *stream);
 
 /* Mean cosine similarity of dense rows A[i] with gathered rows T[idx[i]] (eps = 1e-8 on each norm):
  * HealthRec's knowledge-distillation term `1 - cosine_similarity(item_know, cat(pos_e, neg_e)).mean()`

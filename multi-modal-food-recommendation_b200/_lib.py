@@ -61,6 +61,8 @@ SIGNATURES = {
     "fr_max_row_norm": (C.c_int, [_p, _i64, _i32, _p, _p]),
     "fr_rescore_topk_f32": (C.c_int, [_p, _p, _p, _i32, _f32, _p, _i32, _p, _p, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p]),
     "fr_exact_topk_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _f32, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    "fr_exact_topk_thr_ws_bytes": (_i64, [_i32]),
+    "fr_exact_topk_thr_f32": (C.c_int, [_p, _p, _i32, _p, _i32, _i32, _f32, _p, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "fr_csr_from_coo": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "fr_cosine_mean_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "fr_cosine_mean_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p]),

@@ -161,9 +161,22 @@ rescore_topk_kernel(const float *__restrict__ A, const int64_t *__restrict__ a_r
 // 4 x 4 outputs per thread, k-slices of 16 staged in shared memory (SIMT fp32: this path serves the rare rows whose
 // certificate failed, exactness matters, not throughput).
 constexpr int XT = 64, XK = 16;
+constexpr int LCAP = 512;          // slots of a row's above-threshold list (filtered variant)
+// FILTER: nothing dense is written.  A score goes to the row's list (score, column) only if it reaches the row's
+// threshold `thr[r]` -- a lower bound of the row's k-th best fp32 score, known from the re-scored candidates -- and the
+// column is not in the row's history.  Every member of the fp32 top-k passes; about k + a few columns per row do.
+struct ExactFilter {
+    const float *thr;              // [Mf]
+    float2 *list;                  // [Mf, LCAP] (score, column bits)
+    int *count;                    // [Mf] zeroed; may exceed LCAP (overflow: the caller re-runs the row densely)
+    const int64_t *hist_rows, *hist_ptr;
+    const int32_t *hist_idx;
+};
+template <bool FILTER>
 __global__ void __launch_bounds__(256)
 exact_scores_kernel(const float *__restrict__ A, const int64_t *__restrict__ a_rows, int Mf, const float *__restrict__ B,
-                    int N, int d, float scale, const float *__restrict__ bias, int metric, float *__restrict__ S) {
+                    int N, int d, float scale, const float *__restrict__ bias, int metric, float *__restrict__ S,
+                    const ExactFilter F) {
     __shared__ float As[XK][XT + 4], Bs[XK][XT + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int r0 = blockIdx.y * XT, c0 = blockIdx.x * XT;
@@ -198,11 +211,72 @@ exact_scores_kernel(const float *__restrict__ A, const int64_t *__restrict__ a_r
     for (int i = 0; i < 4; ++i) {
         const int r = r0 + ty * 4 + i;
         if (r >= Mf) continue;
+        const float thr = FILTER ? __ldg(F.thr + r) : 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + tx * 4 + j;
-            if (c < N) S[(size_t)r * N + c] = metric == 0 ? acc[i][j] * scale + (bias ? __ldg(bias + c) : 0.f) : -acc[i][j];
+            if (c >= N) continue;
+            const float sc = metric == 0 ? acc[i][j] * scale + (bias ? __ldg(bias + c) : 0.f) : -acc[i][j];
+            if (!FILTER) {
+                S[(size_t)r * N + c] = sc;
+            } else if (sc >= thr) {
+                bool masked = false;
+                if (F.hist_rows != nullptr) {           // binary search in the row's sorted history
+                    const long long id = F.hist_rows[r];
+                    long long lo = F.hist_ptr[id], hi = F.hist_ptr[id + 1];
+                    while (lo < hi) {
+                        const long long mid = (lo + hi) >> 1;
+                        if (F.hist_idx[mid] < c) lo = mid + 1; else hi = mid;
+                    }
+                    masked = lo < F.hist_ptr[id + 1] && F.hist_idx[lo] == c;
+                }
+                if (!masked) {
+                    const int slot = atomicAdd(F.count + r, 1);
+                    if (slot < LCAP) F.list[(size_t)r * LCAP + slot] = make_float2(sc, __int_as_float(c));
+                }
+            }
         }
+    }
+}
+
+// One CTA per row of the filtered variant: bitonic sort of the row's list by (score desc, column asc) in shared
+// memory, first k out.  Rows whose list overflowed are left untouched and counted in *overflow.
+__global__ void __launch_bounds__(256)
+exact_list_select_kernel(const float2 *__restrict__ list, const int *__restrict__ count, int k,
+                         float *__restrict__ out_val, int64_t *__restrict__ out_idx, int *__restrict__ overflow) {
+    __shared__ unsigned long long key[LCAP];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const int n = count[r];
+    if (n > LCAP) {
+        if (tid == 0) atomicAdd(overflow, 1);
+        return;
+    }
+    for (int i = tid; i < LCAP; i += 256) {
+        unsigned long long kv = 0ull;                    // padding sorts last
+        if (i < n) {
+            const float2 e = list[(size_t)r * LCAP + i];
+            // larger score first, then smaller column first: (order key, ~column) descending
+            kv = ((unsigned long long)order_key(e.x) << 32) | (unsigned)(~__float_as_int(e.y));
+        }
+        key[i] = kv;
+    }
+    __syncthreads();
+    for (int size = 2; size <= LCAP; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < LCAP / 2; i += 256) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long a = key[lo], b = key[hi];
+                if ((a < b) == desc) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    if (tid < k) {
+        const bool have = tid < n;
+        const unsigned long long kv = key[tid];
+        const float v = have ? rk::key_value((unsigned)(kv >> 32)) : -INFINITY;
+        out_val[(size_t)r * k + tid] = v;
+        out_idx[(size_t)r * k + tid] = (have && v != -INFINITY) ? (int64_t)(int)(~(unsigned)(kv & 0xffffffffull)) : -1;
     }
 }
 
@@ -357,7 +431,7 @@ extern "C" int fr_exact_topk_f32(const float *A, const int64_t *a_rows, int32_t 
     dim3 grid((N + XT - 1) / XT, (Mf + XT - 1) / XT);
     {
         fr::LaunchTimer _lt("exact_scores_kernel", st);
-        exact_scores_kernel<<<grid, 256, 0, st>>>(A, a_rows, Mf, B, N, d, scale, bias, metric, scores_ws);
+        exact_scores_kernel<false><<<grid, 256, 0, st>>>(A, a_rows, Mf, B, N, d, scale, bias, metric, scores_ws, ExactFilter{});
         if (int rc = fr::check_launch("fr_exact_topk_f32(scores)")) return rc;
     }
     if (hist_rows != nullptr) {
@@ -368,4 +442,43 @@ extern "C" int fr_exact_topk_f32(const float *A, const int64_t *a_rows, int32_t 
     fr::LaunchTimer _lt("exact_select_kernel", st);
     exact_select_kernel<<<Mf, 256, 0, st>>>(scores_ws, N, k, out_val, out_idx);
     return fr::check_launch("fr_exact_topk_f32(select)");
+}
+
+extern "C" int64_t fr_exact_topk_thr_ws_bytes(int32_t Mf) { return (int64_t)Mf * (LCAP * 8 + 4); }
+
+extern "C" int fr_exact_topk_thr_f32(const float *A, const int64_t *a_rows, int32_t Mf, const float *B, int32_t N, int32_t d,
+                                     float scale, const float *bias, int32_t metric, const int64_t *hist_rows,
+                                     const int64_t *hist_ptr, const int32_t *hist_idx, int32_t k, const float *thr, void *ws,
+                                     float *out_val, int64_t *out_idx, int32_t *overflow, void *stream) {
+    FR_REQUIRE(Mf >= 0 && N > 0 && d > 0 && d % 4 == 0, "fr_exact_topk_thr_f32: Mf=%d N=%d d=%d", Mf, N, d);
+    if (Mf == 0) return FR_OK;
+    FR_REQUIRE(A && a_rows && B && thr && ws && out_val && out_idx && overflow, "fr_exact_topk_thr_f32: null pointer");
+    FR_REQUIRE(k >= 1 && k <= rk::MAXK, "fr_exact_topk_thr_f32: k=%d out of [1, %d]", k, rk::MAXK);
+    FR_REQUIRE(metric == 0 || metric == 1, "fr_exact_topk_thr_f32: metric=%d", metric);
+    FR_REQUIRE((hist_rows == nullptr) == (hist_ptr == nullptr) && (hist_rows == nullptr) == (hist_idx == nullptr),
+               "fr_exact_topk_thr_f32: hist_rows / hist_ptr / hist_idx go together");
+    FR_REQUIRE(((uintptr_t)ws & 7) == 0, "fr_exact_topk_thr_f32: workspace must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    ExactFilter F;
+    F.thr = thr;
+    F.list = reinterpret_cast<float2 *>(ws);
+    F.count = reinterpret_cast<int *>(F.list + (size_t)Mf * LCAP);
+    F.hist_rows = hist_rows;
+    F.hist_ptr = hist_ptr;
+    F.hist_idx = hist_idx;
+    cudaError_t e = cudaMemsetAsync(F.count, 0, (size_t)Mf * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(overflow, 0, sizeof(int), st);
+    if (e != cudaSuccess) {
+        fr::set_error("fr_exact_topk_thr_f32: %s", cudaGetErrorString(e));
+        return FR_ECUDA;
+    }
+    dim3 grid((N + XT - 1) / XT, (Mf + XT - 1) / XT);
+    {
+        fr::LaunchTimer _lt("exact_scores_kernel<filter>", st);
+        exact_scores_kernel<true><<<grid, 256, 0, st>>>(A, a_rows, Mf, B, N, d, scale, bias, metric, nullptr, F);
+        if (int rc = fr::check_launch("fr_exact_topk_thr_f32(scores)")) return rc;
+    }
+    fr::LaunchTimer _lt("exact_list_select_kernel", st);
+    exact_list_select_kernel<<<Mf, 256, 0, st>>>(F.list, F.count, k, out_val, out_idx, overflow);
+    return fr::check_launch("fr_exact_topk_thr_f32(select)");
 }

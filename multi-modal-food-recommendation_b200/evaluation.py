@@ -117,14 +117,32 @@ def max_row_norm(B: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def exact_topk_rows(A, rows, B, k, *, scale=1.0, bias=None, metric=0, row_ids=None, hist=None, max_ws_bytes=1 << 30):
-    """fp32 top-k of rows `A[rows]` against every row of B on the CUDA cores (`fr_exact_topk_f32`): the path for
-    rows whose certificate failed.  Returns (values `[len(rows), k]`, int64 indices)."""
+def exact_topk_rows(A, rows, B, k, *, scale=1.0, bias=None, metric=0, row_ids=None, hist=None, max_ws_bytes=1 << 30,
+                    thr=None):
+    """fp32 top-k of rows `A[rows]` against every row of B on the CUDA cores: the path for rows whose certificate
+    failed.  Returns (values `[len(rows), k]`, int64 indices).
+
+    `thr` (`[len(rows)]`, optional): a lower bound of each row's k-th best fp32 score.  With it the scoring pass keeps
+    only the columns that reach the bound (`fr_exact_topk_thr_f32`: per-row lists instead of a dense `[rows, N]` score
+    block and five passes over it); rows whose list overflows (massive ties) are redone densely (`fr_exact_topk_f32`)."""
     dev, N, K = A.device, B.shape[0], B.shape[1]
     rows = rows.to(torch.int64).contiguous()
     n = rows.numel()
     out_v = torch.empty((n, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((n, k), dtype=torch.int64, device=dev)
+    if thr is not None and n:
+        hr = (row_ids[rows] if row_ids is not None else rows).to(torch.int64).contiguous() if hist is not None else None
+        ws = torch.empty(int(_L.fr_exact_topk_thr_ws_bytes(n)), dtype=torch.uint8, device=dev)
+        over = torch.empty(1, dtype=torch.int32, device=dev)
+        thr = thr.to(torch.float32).contiguous()
+        _lib.check(_L.fr_exact_topk_thr_f32(
+            A.data_ptr(), rows.data_ptr(), n, B.data_ptr(), N, K, float(scale), _lib.ptr(bias), int(metric),
+            _lib.ptr(hr), hist.ptr.data_ptr() if hist is not None else None,
+            hist.idx.data_ptr() if hist is not None else None, k, thr.data_ptr(), ws.data_ptr(), out_v.data_ptr(),
+            out_i.data_ptr(), over.data_ptr(), _lib.stream_ptr()), "fr_exact_topk_thr_f32")
+        if int(over.item()) == 0:
+            return out_v, out_i
+        # some list overflowed: those rows' outputs were left untouched -- redo every row densely (rare: massive ties)
     chunk = max(1, min(n, max_ws_bytes // (4 * N)))
     ws = torch.empty(chunk * N, dtype=torch.float32, device=dev)
     hrows = None
@@ -141,7 +159,7 @@ def exact_topk_rows(A, rows, B, k, *, scale=1.0, bias=None, metric=0, row_ids=No
 
 
 def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, bias: torch.Tensor | None = None,
-              row_ids: torch.Tensor | None = None, hist: HistoryCSR | None = None, slack: int = 12,
+              row_ids: torch.Tensor | None = None, hist: HistoryCSR | None = None, slack: int | None = None,
               exact: bool = True, metric: int = 0, A_bf16: torch.Tensor | None = None,
               B_bf16: torch.Tensor | None = None, index_dtype=torch.int64, b_max_norm: torch.Tensor | None = None,
               stats: dict | None = None):
@@ -152,7 +170,13 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
     tensor-core pass are re-scored in fp32, every row is checked against the rounding-error certificate
     (`fr_rescore_topk_f32`), rows that fail are re-ranked with the widest candidate set and, if they fail
     again, scored exactly against every column (`fr_exact_topk_f32`).  `stats` (a dict) receives how many rows
-    took each path.  `exact=False` returns the bf16-scored top-k without re-score."""
+    took each path.  `exact=False` returns the bf16-scored top-k without re-score.
+
+    `slack` = extra candidates the tensor-core pass keeps per row (`kc = k + slack`).  Every extra candidate costs
+    ~0.7 % of the kernel time (measured on the 1 M x 500 k shape: kc = 32 / 40 / 48 / 64 -> 14.2 / 15.0 / 15.8 / 17.7 ms
+    per 125 000 rows) while the rows a narrow `kc` leaves uncertified cost a fixed 3.5 - 5 ms of fallback passes
+    (`scripts/microbench_c4_slack.py`); with kc = k + 20 no row of that shape needs a fallback.  Default: 20 when the
+    launch is short enough for the fixed cost to matter (< ~45 ms of tensor-core time), else 12."""
     if k < 1 or k > MAX_K:
         raise _lib.FoodRecError(f"k={k} outside [1, {MAX_K}]")
     if index_dtype not in (torch.int64, torch.int32):
@@ -167,6 +191,8 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
     Ab = A_bf16 if A_bf16 is not None else to_bf16(A)
     Bb = B_bf16 if B_bf16 is not None else to_bf16(B)
     kk = min(k, N)
+    if slack is None:
+        slack = 20 if 2.0 * M * N * K < 45e-3 * 5.5e14 else 12       # ~550 TFLOP/s at K = 64
     kc = min(MAX_K, kk + max(int(slack), 0), N) if exact else kk
     if hist is not None:
         if row_ids is None:
@@ -197,7 +223,13 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
             bad = bad[cert2 == 0]
         n_exact = int(bad.numel())
         if n_exact:
-            v3, i3 = exact_topk_rows(A, bad, B, kk, scale=scale, bias=bias, metric=metric, row_ids=row_ids, hist=hist)
+            # every member of the fp32 top-k scores at least the k-th best re-scored value; the margin covers the
+            # different fp32 summation orders of the two kernels (K 2^-24 |a| max|b|, doubled)
+            margin = max(1e-5, 2.0 * K * 2.0 ** -24)
+            vk = out_v[bad, kk - 1]
+            thr = vk - margin * (vk.abs() + (A[bad].norm(dim=1) * bmax[0] * abs(float(scale)) if metric == 0 else 0.0))
+            v3, i3 = exact_topk_rows(A, bad, B, kk, scale=scale, bias=bias, metric=metric, row_ids=row_ids, hist=hist,
+                                     thr=thr)
             out_v[bad] = v3
             out_i[bad] = i3.to(index_dtype)
     if stats is not None:

@@ -310,3 +310,10 @@ def test_exact_fp32_row_kernel(metric):
     # fewer eligible columns than k: padded with -1 / -inf
     tiny_v, tiny_i = E.exact_topk_rows(A.cuda(), rows[:2].cuda(), B[:10].cuda(), 33, metric=metric)
     assert tiny_i.shape == (2, 33) and int((tiny_i >= 0).sum()) == 20 and bool(torch.isinf(tiny_v[:, 10:]).all())
+    # thresholded variant (`fr_exact_topk_thr_f32`): a lower bound of the k-th best score per row -> same result, no
+    # dense score block; a useless bound (-inf: every column qualifies, the lists overflow) falls back to the dense path
+    kth = torch.topk(S, k, dim=1)[0][:, -1]
+    for thr in (kth - 1e-3 * kth.abs() - 1e-3, torch.full_like(kth, -float("inf"))):
+        v2, i2 = E.exact_topk_rows(A.cuda(), rows.cuda(), B.cuda(), k, scale=0.5 if metric == 0 else 1.0,
+                                   bias=None if bias is None else bias.cuda(), metric=metric, hist=hist, thr=thr.cuda())
+        assert torch.equal(i2.cpu(), i) and torch.equal(v2, v)

@@ -180,8 +180,11 @@ def test_row_masks_survive_cross_stream_backward():
             torch.cuda.synchronize()
             for x, y in zip(ga, gb):
                 # dense-atomic accumulation order differs run to run in the loss kernels, not in the propagation:
-                # compare with the tolerance of fp32 atomics, and exactly where the gradient is structurally zero
-                assert torch.equal(x == 0, y == 0), it
+                # compare with the tolerance of fp32 atomics.  A dropped gather would zero WHOLE rows of one run, so the
+                # zero patterns must agree row-wise; single elements may cancel to exactly 0 in one summation order and
+                # to 1 ulp in another (seen once in ~90 iterations), which the tolerance below covers.
+                mism = (x == 0) != (y == 0)
+                assert not bool(mism.reshape(x.shape[0], -1).all(dim=1).any()) and int(mism.sum()) <= 8, (it, int(mism.sum()))
                 assert torch.allclose(x, y, rtol=1e-5, atol=1e-9), it
             junk.clear()
     finally:

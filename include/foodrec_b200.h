@@ -308,6 +308,16 @@ int fr_schgn_attend(const float *user_key, const float *user_comp, int32_t nu, c
 int fr_schgn_score(const float *user_final, const float *user_hidden, int32_t nu, const float *W_item,
                    const float *W_prod, const float *w_out, const float *comps, const float *att, const float *logits,
                    int32_t n_items, int32_t d, float *scores, void *stream);
+/* fr_schgn_score with the row-wise top-k fused in: the [nu, I] score block never reaches HBM.  Each CTA keeps the k best
+ * of its 256 items (bitonic sort in shared memory; `user_ids[nu]` + the sorted history CSR exclude each user's training
+ * items, NULL = no mask as in the reference, trainer.py:495-497), a second launch merges the block winners per user.
+ * Output: out_val / out_idx [nu, k], score descending, ties to the lower item; -inf / -1 when fewer than k items remain.
+ * ws: fr_schgn_score_topk_ws_bytes(nu, n_items, k) bytes, 8-byte aligned.  k <= 64. */
+int64_t fr_schgn_score_topk_ws_bytes(int32_t nu, int32_t n_items, int32_t k);
+int fr_schgn_score_topk(const float *user_final, const float *user_hidden, int32_t nu, const float *W_item,
+                        const float *W_prod, const float *w_out, const float *comps, const float *att, const float *logits,
+                        int32_t n_items, int32_t d, const int64_t *user_ids, const int64_t *hist_ptr,
+                        const int32_t *hist_idx, int32_t k, void *ws, float *out_val, int64_t *out_idx, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-partitioned multi-GPU propagation over peer memory (one process per GPU, one NVLink/NVSwitch node).

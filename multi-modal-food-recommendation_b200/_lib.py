@@ -88,6 +88,8 @@ SIGNATURES = {
     "fr_sample_negatives": (C.c_int, [_p, _p, _p, _i64, _i32, C.c_uint64, C.c_uint64, _p, _p, _p]),
     "fr_schgn_attend": (C.c_int, [_p, _p, _i32, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "fr_schgn_score": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p]),
+    "fr_schgn_score_topk_ws_bytes": (_i64, [_i32, _i32, _i32]),
+    "fr_schgn_score_topk": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p]),
 }
 
 class SpmmTask(C.Structure):

@@ -178,7 +178,37 @@ struct ScoreParams {
     const float *user_final, *user_hidden, *W_item, *W_prod, *w_out, *comps, *att, *logits;
     float *scores;
     int32_t nu, n_items;
+    // fused top-k mode (TOPK): instead of the dense scores, each CTA keeps the kt best of its 256 items as sortable
+    // 64-bit keys [nu, n_blocks, kt]; `user_ids` + the history CSR mask training items (NULL: no mask, as the reference)
+    unsigned long long *cand;
+    const int64_t *user_ids, *hist_ptr;
+    const int32_t *hist_idx;
+    int32_t kt;
 };
+
+// (score desc, column asc) as ONE descending 64-bit key; 0 = absent
+__device__ __forceinline__ unsigned long long topk_key(float score, int col) {
+    const unsigned u = __float_as_uint(score);
+    const unsigned ok = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)ok << 32) | (unsigned)(~col);
+}
+__device__ __forceinline__ float key_score(unsigned long long k) {
+    const unsigned ok = (unsigned)(k >> 32);
+    return __uint_as_float((ok & 0x80000000u) ? (ok & 0x7fffffffu) : ~ok);
+}
+// descending bitonic sort of `n` (power of two) keys in shared memory by the whole CTA
+__device__ __forceinline__ void bitonic_desc(unsigned long long *key, int n, int tid, int nthreads) {
+    for (int size = 2; size <= n; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < n / 2; i += nthreads) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long a = key[lo], b = key[hi];
+                if ((a < b) == desc) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+}
 
 constexpr int SC_THREADS = 128;
 constexpr int IPT = 2;                      // items per thread
@@ -186,6 +216,7 @@ constexpr int SC_ITEMS = SC_THREADS * IPT;  // items per CTA
 constexpr int XS = D + 4;                   // row stride of the x tile (floats): conflict-free LDS.128 per quarter-warp
 constexpr int SC_SMEM = (SC_ITEMS * XS + D * D + 2 * D + SC_ITEMS * 4) * (int)sizeof(float);
 
+template <bool TOPK>
 __global__ void __launch_bounds__(SC_THREADS) schgn_score_kernel(const ScoreParams p) {
     extern __shared__ __align__(16) float smem[];
     float *sX = smem;                    // [SC_ITEMS][XS]   x = B-weighted component mix, one row per item
@@ -264,10 +295,65 @@ __global__ void __launch_bounds__(SC_THREADS) schgn_score_kernel(const ScorePara
         for (int t = 0; t < IPT; ++t)
             score[t] = fmaf(w, fmaxf((h[t][0] + h[t][1]) + (h[t][2] + h[t][3]), 0.0f), score[t]);
     }
+    if (!TOPK) {
+#pragma unroll
+        for (int t = 0; t < IPT; ++t) {
+            const int r = base + tid + t * SC_THREADS;
+            if (r < p.n_items) p.scores[(size_t)u * p.n_items + r] = score[t];
+        }
+        return;
+    }
+    // ---- fused top-k: this CTA's 256 scores -> the kt best as keys; the [users, items] block never reaches HBM
+    __syncthreads();                                   // every thread has its x rows in registers: the tile can be reused
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(sX);
+    long long h0 = 0, h1 = 0;
+    if (p.user_ids != nullptr) {
+        const long long id = p.user_ids[u];
+        h0 = p.hist_ptr[id];
+        h1 = p.hist_ptr[id + 1];
+    }
 #pragma unroll
     for (int t = 0; t < IPT; ++t) {
         const int r = base + tid + t * SC_THREADS;
-        if (r < p.n_items) p.scores[(size_t)u * p.n_items + r] = score[t];
+        bool dead = r >= p.n_items;
+        if (!dead && h1 > h0) {                        // binary search in the user's sorted training items
+            long long lo = h0, hi = h1;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if (p.hist_idx[mid] < r) lo = mid + 1; else hi = mid;
+            }
+            dead = lo < h1 && p.hist_idx[lo] == r;
+        }
+        key[tid + t * SC_THREADS] = dead ? 0ull : topk_key(score[t], r);
+    }
+    __syncthreads();
+    bitonic_desc(key, SC_ITEMS, tid, SC_THREADS);
+    if (tid < p.kt) p.cand[((size_t)u * gridDim.x + blockIdx.x) * p.kt + tid] = key[tid];
+}
+
+// One CTA per user: the n_cand = n_blocks * kt block winners -> the k best, (score desc, column asc).  The running
+// best stays in the first k slots of a 2048-key shared tile while the candidates stream through the rest.
+constexpr int MG_TILE = 2048;
+__global__ void __launch_bounds__(256)
+schgn_merge_topk_kernel(const unsigned long long *__restrict__ cand, int n_cand, int k, float *__restrict__ out_val,
+                        int64_t *__restrict__ out_idx) {
+    __shared__ unsigned long long key[MG_TILE];
+    const int u = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long *c = cand + (size_t)u * n_cand;
+    int pos = 0, keep = 0;
+    while (pos < n_cand || keep == 0) {
+        const int take = min(MG_TILE - keep, n_cand - pos);
+        for (int i = tid; i < MG_TILE - keep; i += 256) key[keep + i] = i < take ? c[pos + i] : 0ull;
+        __syncthreads();
+        bitonic_desc(key, MG_TILE, tid, 256);
+        pos += take;
+        keep = k;
+        if (take <= 0) break;
+    }
+    if (tid < k) {
+        const unsigned long long kv = key[tid];
+        out_val[(size_t)u * k + tid] = kv ? key_score(kv) : -INFINITY;
+        out_idx[(size_t)u * k + tid] = kv ? (int64_t)(int)(~(unsigned)(kv & 0xffffffffull)) : -1;
     }
 }
 
@@ -304,16 +390,57 @@ extern "C" int fr_schgn_score(const float *user_final, const float *user_hidden,
     if (nu == 0 || n_items == 0) return FR_OK;
     FR_REQUIRE(user_final && user_hidden && W_item && W_prod && w_out && comps && att && logits && scores,
                "fr_schgn_score: null pointer");
-    ScoreParams p{user_final, user_hidden, W_item, W_prod, w_out, comps, att, logits, scores, nu, n_items};
+    ScoreParams p{user_final, user_hidden, W_item, W_prod, w_out, comps, att, logits, scores, nu, n_items,
+                  nullptr, nullptr, nullptr, nullptr, 0};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     fr::LaunchTimer timer("schgn_score", st);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(schgn_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(schgn_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM) != cudaSuccess)
             return fr::check_launch("fr_schgn_score (shared-memory opt-in)");
         configured = true;
     }
     dim3 grid((n_items + SC_ITEMS - 1) / SC_ITEMS, nu);
-    schgn_score_kernel<<<grid, SC_THREADS, SC_SMEM, st>>>(p);
+    schgn_score_kernel<false><<<grid, SC_THREADS, SC_SMEM, st>>>(p);
     return fr::check_launch("fr_schgn_score");
+}
+
+extern "C" int64_t fr_schgn_score_topk_ws_bytes(int32_t nu, int32_t n_items, int32_t k) {
+    return (int64_t)nu * ((n_items + SC_ITEMS - 1) / SC_ITEMS) * k * 8;
+}
+
+extern "C" int fr_schgn_score_topk(const float *user_final, const float *user_hidden, int32_t nu, const float *W_item,
+                                   const float *W_prod, const float *w_out, const float *comps, const float *att,
+                                   const float *logits, int32_t n_items, int32_t d, const int64_t *user_ids,
+                                   const int64_t *hist_ptr, const int32_t *hist_idx, int32_t k, void *ws, float *out_val,
+                                   int64_t *out_idx, void *stream) {
+    FR_REQUIRE(d == D, "fr_schgn_score_topk: embedding width %d unsupported (the model fixes 64)", d);
+    FR_REQUIRE(nu >= 0 && nu <= 65535 && n_items >= 0, "fr_schgn_score_topk: bad extents (nu=%d, n_items=%d)", nu, n_items);
+    FR_REQUIRE(k >= 1 && k <= 64, "fr_schgn_score_topk: k=%d out of [1, 64]", k);
+    if (nu == 0) return FR_OK;
+    FR_REQUIRE(n_items > 0, "fr_schgn_score_topk: no items");
+    FR_REQUIRE(user_final && user_hidden && W_item && W_prod && w_out && comps && att && logits && ws && out_val && out_idx,
+               "fr_schgn_score_topk: null pointer");
+    FR_REQUIRE((user_ids == nullptr) == (hist_ptr == nullptr) && (user_ids == nullptr) == (hist_idx == nullptr),
+               "fr_schgn_score_topk: user_ids / hist_ptr / hist_idx go together");
+    FR_REQUIRE(((uintptr_t)ws & 7) == 0, "fr_schgn_score_topk: workspace must be 8-byte aligned");
+    ScoreParams p{user_final, user_hidden, W_item, W_prod, w_out, comps, att, logits, nullptr, nu, n_items,
+                  reinterpret_cast<unsigned long long *>(ws), user_ids, hist_ptr, hist_idx, k};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(schgn_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM) != cudaSuccess)
+            return fr::check_launch("fr_schgn_score_topk (shared-memory opt-in)");
+        configured = true;
+    }
+    const int n_blk = (n_items + SC_ITEMS - 1) / SC_ITEMS;
+    {
+        fr::LaunchTimer timer("schgn_score<topk>", st);
+        dim3 grid(n_blk, nu);
+        schgn_score_kernel<true><<<grid, SC_THREADS, SC_SMEM, st>>>(p);
+        if (int rc = fr::check_launch("fr_schgn_score_topk(score)")) return rc;
+    }
+    fr::LaunchTimer timer("schgn_merge_topk", st);
+    schgn_merge_topk_kernel<<<nu, 256, 0, st>>>(p.cand, n_blk * k, k, out_val, out_idx);
+    return fr::check_launch("fr_schgn_score_topk(merge)");
 }

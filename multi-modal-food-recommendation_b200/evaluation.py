@@ -322,11 +322,15 @@ def centroid_topk(features: torch.Tensor, centres: torch.Tensor, k: int = 6, **k
 
 # ------------------------------------------------------------------------------ by-user evaluation
 def schgn_pair_scores(*, user_final, user_key, user_comp, user_hidden, W_item, W_prod, w_out, h_ingre, h_comp, codes,
-                      nums, ingre_key, ingre_final, ingre_comp, img_key, comps, comp_keys) -> torch.Tensor:
+                      nums, ingre_key, ingre_final, ingre_comp, img_key, comps, comp_keys, topk: int | None = None,
+                      user_ids: torch.Tensor | None = None, hist: HistoryCSR | None = None):
     """SCHGN scores `[nu, n_items]` of `nu` users against every item from the user-independent tables
     (`models.schgn.SCHGN._item_side`): `fr_schgn_attend` + `fr_schgn_score`, FoodRec/models/schgn.py:159-206,
     233-268, 318-345.  Users are processed in blocks so the `[nu, I, 64]` attended-row scratch stays
-    under ~1 GB."""
+    under ~1 GB.
+
+    `topk=k`: returns `(values [nu, k], int64 indices [nu, k])` instead, with the selection fused into the scorer
+    (`fr_schgn_score_topk`) -- the score block is never written; `hist` + `user_ids` mask each user's training items."""
     dev = user_final.device
     if dev.type != "cuda":
         raise _lib.FoodRecError("schgn_pair_scores needs CUDA tensors (no CPU path)")
@@ -338,8 +342,20 @@ def schgn_pair_scores(*, user_final, user_key, user_comp, user_hidden, W_item, W
     n_items, slots = codes.shape
     if codes.dtype != torch.int32 or nums.dtype != torch.int32:
         raise _lib.FoodRecError("ingredient codes / counts must be int32")
-    scores = torch.empty(nu, n_items, dtype=torch.float32, device=dev)
+    if topk is not None:
+        if not 1 <= topk <= MAX_K:
+            raise _lib.FoodRecError(f"k={topk} outside [1, {MAX_K}]")
+        out_v = torch.empty(nu, topk, dtype=torch.float32, device=dev)
+        out_i = torch.empty(nu, topk, dtype=torch.int64, device=dev)
+        if hist is not None:
+            if user_ids is None:
+                raise _lib.FoodRecError("a history mask needs the users' ids")
+            user_ids = user_ids.to(device=dev, dtype=torch.int64).contiguous()
+    else:
+        scores = torch.empty(nu, n_items, dtype=torch.float32, device=dev)
     block = max(16, min(256, (1 << 30) // max(1, n_items * d * 4) // 16 * 16))
+    if topk is not None:
+        ws = torch.empty(int(_L.fr_schgn_score_topk_ws_bytes(min(block, nu), n_items, topk)), dtype=torch.uint8, device=dev)
     att = torch.empty(min(block, nu), n_items, d, dtype=torch.float32, device=dev)
     logits = torch.empty(min(block, nu), 4, n_items, dtype=torch.float32, device=dev)
     st = _lib.stream_ptr()
@@ -350,11 +366,19 @@ def schgn_pair_scores(*, user_final, user_key, user_comp, user_hidden, W_item, W
             ingre_key.data_ptr(), ingre_final.data_ptr(), ingre_comp.data_ptr(), img_key.data_ptr(),
             comp_keys.data_ptr(), h_ingre.data_ptr(), h_comp.data_ptr(), d, att.data_ptr(),
             logits.data_ptr(), st), "fr_schgn_attend")
-        _lib.check(_L.fr_schgn_score(
-            user_final[s:].data_ptr(), user_hidden[s:].data_ptr(), n, W_item.data_ptr(), W_prod.data_ptr(),
-            w_out.data_ptr(), comps.data_ptr(), att.data_ptr(), logits.data_ptr(), n_items, d,
-            scores[s:].data_ptr(), st), "fr_schgn_score")
-    return scores
+        if topk is None:
+            _lib.check(_L.fr_schgn_score(
+                user_final[s:].data_ptr(), user_hidden[s:].data_ptr(), n, W_item.data_ptr(), W_prod.data_ptr(),
+                w_out.data_ptr(), comps.data_ptr(), att.data_ptr(), logits.data_ptr(), n_items, d,
+                scores[s:].data_ptr(), st), "fr_schgn_score")
+        else:
+            _lib.check(_L.fr_schgn_score_topk(
+                user_final[s:].data_ptr(), user_hidden[s:].data_ptr(), n, W_item.data_ptr(), W_prod.data_ptr(),
+                w_out.data_ptr(), comps.data_ptr(), att.data_ptr(), logits.data_ptr(), n_items, d,
+                user_ids[s:].data_ptr() if hist is not None else None, hist.ptr.data_ptr() if hist is not None else None,
+                hist.idx.data_ptr() if hist is not None else None, topk, ws.data_ptr(), out_v[s:].data_ptr(),
+                out_i[s:].data_ptr(), st), "fr_schgn_score_topk")
+    return scores if topk is None else (out_v, out_i)
 
 
 def evaluate_by_user(model, users, cand_ptr, cand_items, n_pos, neg_num: int = 500):

@@ -285,14 +285,17 @@ class SCHGN(GeneralRecommender):
         return cache
 
     @torch.no_grad()
-    def full_sort_scores(self, users: torch.Tensor) -> torch.Tensor:
-        """Scores `[n_users_in_batch, n_items]` of the given users against every item."""
+    def full_sort_scores(self, users: torch.Tensor, topk: int | None = None, hist=None):
+        """Scores `[n_users_in_batch, n_items]` of the given users against every item; with `topk=k` the fused
+        selection `(values [n, k], indices [n, k])` instead (the score block is never materialised)."""
         from .. import evaluation
         c = self._item_side()
         e = self.emb_size
-        u = c["user_final"][users.to(c["user_final"].device).long()]
+        users = users.to(c["user_final"].device).long().reshape(-1)
+        u = c["user_final"][users]
         Wk, bk = self.W_concat.weight, self.W_concat.bias               # [e, 3e]: user | item | user * item
         return evaluation.schgn_pair_scores(
+            topk=topk, user_ids=users, hist=hist,
             user_final=u, user_key=u @ c["Wi_user"], user_comp=u @ c["Wc_user"] + c["bc"],
             user_hidden=u @ Wk[:, :e].t() + bk, W_item=Wk[:, e:2 * e].contiguous(), W_prod=Wk[:, 2 * e:].contiguous(),
             w_out=self.output_mlp.weight.reshape(-1).contiguous(), h_ingre=self.h_att_ingre.weight.reshape(-1),
@@ -308,8 +311,17 @@ class SCHGN(GeneralRecommender):
 
     @torch.no_grad()
     def full_sort_topk(self, users: torch.Tensor, k: int, hist=None, block: int = 256):
-        """Top-k items per user (values, int64 indices), users scored 16 per launch pair; `hist`
-        (`evaluation.HistoryCSR`) masks training interactions (the reference does not mask)."""
+        """Top-k items per user (values, int64 indices; score descending, ties to the lower item), 16 users per pass
+        of the attention kernel, the selection fused into the scorer (`fr_schgn_score_topk`): `[users, items]` scores
+        never reach HBM.  `hist` (`evaluation.HistoryCSR`) masks training interactions (the reference does not mask).
+        `k` beyond the kernel's 64 falls back to dense scores + `torch.topk`."""
+        users = users.reshape(-1)
+        if k <= min(64, self.n_items):
+            return self.full_sort_scores(users, topk=k, hist=hist)
+        return self._full_sort_topk_dense(users, k, hist, block)
+
+    @torch.no_grad()
+    def _full_sort_topk_dense(self, users, k, hist, block):
         vals, idx = [], []
         for s in range(0, users.numel(), block):
             ub = users[s:s + block]

@@ -121,6 +121,32 @@ def test_c1_full_sort_matches_oracle_and_topk_with_mask(c1_model):
     assert torch.equal(i2, torch.topk(m.full_sort_scores(users), k).indices)
 
 
+@pytest.mark.parametrize("k", [1, 20, 50, 64])
+def test_fused_topk_equals_dense_scores_then_topk(c1_model, k):
+    """`fr_schgn_score_topk` (selection fused into the scorer, `[users, items]` never written) against the dense
+    scores of `fr_schgn_score` + mask + `torch.topk`, for users spanning several 16-user passes: identical values, and
+    identical indices wherever the k-th score is not tied."""
+    from foodrec_b200 import evaluation
+    m, ds = c1_model
+    users = torch.arange(3, 3 + 53 * 41, 41, device="cuda") % ds.n_users            # 53 users
+    hist = evaluation.HistoryCSR(ds.train_coo_matrix, ds.n_users, "cuda")
+    for h in (None, hist):
+        dense = m.full_sort_scores(users)
+        if h is not None:
+            h.mask_scores_(dense, users)
+        rv, ri = torch.topk(dense, k, dim=-1)
+        v, i = m.full_sort_topk(users, k, hist=h)
+        assert v.shape == (users.numel(), k) and i.dtype == torch.int64
+        assert torch.equal(v, rv)                                   # same kernel arithmetic: bit-identical scores
+        assert torch.equal(torch.gather(dense, 1, i), v)            # every index carries its score
+        untied = (rv[:, :-1] != rv[:, 1:]).all(dim=1) if k > 1 else torch.ones(users.numel(), dtype=torch.bool, device="cuda")
+        assert torch.equal(i[untied], ri[untied])
+        # ties go to the lower item id
+        assert bool(((v[:, :-1] > v[:, 1:]) | (i[:, :-1] < i[:, 1:])).all()) if k > 1 else True
+    v70, i70 = m.full_sort_topk(users[:5], 70)                      # beyond the kernel's 64: dense fallback
+    assert torch.equal(i70, torch.topk(m.full_sort_scores(users[:5]), 70).indices)
+
+
 def test_c1_evaluate_full_sort_metrics_match_oracle_ranking(c1_model):
     """`evaluation.evaluate_full_sort` on SCHGN (the reference's `Trainer.evaluate` loop, no mask): Recall /
     NDCG / Precision / MAP @5/10/20/50 over 64 users equal those of the CPU restatement's ranking to 4 d.p."""

@@ -372,16 +372,22 @@ def main():
 
     # ---- e2e: pinned host batches in, loss terms out, through the public model API
     h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    graphed = step_mode == "cuda_graph_replay"
+
+    def e2e_step(host_batch):
+        if graphed:       # pinned host tensors -> the graph's static inputs (H2D), replay, all loss terms in one D2H
+            step(host_batch)
+            return step.loss_values()
+        losses = step({k: v.to(dev, non_blocking=True) for k, v in host_batch.items()})
+        return [float(x.item()) for x in losses]  # trainer.py:186: per-term .item()
     for i in range(2):
-        step({k: v.to(dev, non_blocking=True) for k, v in pinned[i % len(pinned)].items()})
+        e2e_step(pinned[i % len(pinned)])
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     n_e2e = max(args.steps, min(timed_steps, 400))
     for i in range(n_e2e):
-        b = {k: v.to(dev, non_blocking=True) for k, v in pinned[(args.warmup + i) % len(pinned)].items()}
-        losses = step(b)
-        vals = [float(x.item()) for x in losses]  # trainer.py:186: per-term .item()
+        vals = e2e_step(pinned[(args.warmup + i) % len(pinned)])
         d2h = 4 * len(vals)
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / n_e2e

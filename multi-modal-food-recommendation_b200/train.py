@@ -149,15 +149,23 @@ class GraphedTrainStep:
             if grad_hook is not None:
                 grad_hook(model)
             optimizer.step()
-        self.losses = losses if isinstance(losses, tuple) else (losses,)
-        self.loss_vec = None
+            self.losses = losses if isinstance(losses, tuple) else (losses,)
+            # every term in one device vector (inside the graph), so a trainer reads them with ONE device->host copy
+            self.loss_vec = torch.stack([l.detach().reshape(()).float() for l in self.losses])
 
     def __call__(self, batch: dict):
+        """`batch` tensors may live on the device or in (pinned) host memory: they are copied straight into the
+        static inputs of the graph."""
         for k in self.keys:
             self.static[k].copy_(batch[k], non_blocking=True)
         self.graph.replay()
         mark_parameters_updated(self.model)
         return self.losses
+
+    def loss_values(self):
+        """The loss terms of the last replay as python floats: one synchronising device->host copy for all of them
+        (the reference trainer's per-term `.item()`, trainer.py:186, costs one round trip per term)."""
+        return self.loss_vec.tolist()
 
 
 class DeviceBatchSampler:

@@ -70,9 +70,16 @@ def test_graph_replay_step_equals_eager_step():
         l2 = [float(x) for x in g(b)]
         for a, c in zip(l1, l2):
             assert abs(a - c) <= 1e-5 * max(abs(a), 1e-6), (l1, l2)
+        assert g.loss_values() == l2         # all terms through one device->host copy
     for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         diff = (p1 - p2).abs()   # fp32 atomics order differs run to run; Adam turns that into rare +-lr moves
         assert float((diff > 2e-5).float().mean()) < 0.01, (n1, float((diff > 2e-5).float().mean()))
+    # pinned host batches go straight into the graph's static inputs
+    host = {k: v.cpu().pin_memory() for k, v in dev[1].items()}
+    a = [float(x) for x in g(host)]
+    b2 = [float(x) for x in g(dev[1])]
+    for x, y in zip(a, b2):
+        assert abs(x - y) <= 0.05 * abs(y)   # (one more Adam step in between: same batch, nearly the same losses)
 
 
 def test_device_sampler_negatives_are_admissible_uniform_and_reproducible(mini_ds):

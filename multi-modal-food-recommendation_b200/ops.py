@@ -287,6 +287,10 @@ class _PropagateMeanGrouped(torch.autograd.Function):
         n = len(group.graphs)
         tops, bottoms = [t.contiguous() for t in tabs[:n]], [t.contiguous() for t in tabs[n:]]
         ctx.group, ctx.n_layers, ctx.n_top = group, n_layers, [t.shape[0] for t in tops]
+        # CLUSSL feeds the SAME item table to every graph of the group (pricai_modelx.py:181,195,209): its gradient is
+        # then the sum of the graphs' top blocks, produced by one `fr_sum_rows` launch in the backward instead of
+        # autograd's chain of elementwise adds
+        ctx.shared_top = n > 1 and all(t.data_ptr() == tops[0].data_ptr() and t.shape == tops[0].shape for t in tops)
         return tuple(_propagate_mean_grouped_raw(group, tops, bottoms, n_layers))
 
     @staticmethod
@@ -304,6 +308,10 @@ class _PropagateMeanGrouped(torch.autograd.Function):
         r = _propagate_mean_grouped_raw(gt, gs, [None] * len(gs), ctx.n_layers)
         tops = [x[:nt] for x, nt in zip(r, ctx.n_top)]
         bottoms = [x[nt:] for x, nt in zip(r, ctx.n_top)]
+        if ctx.shared_top:
+            total = torch.empty((ctx.n_top[0], d), dtype=torch.float32, device=r[0].device)
+            _lib.check(_L.fr_sum_rows(_ptr_array(r), len(r), d, ctx.n_top[0], total.data_ptr(), _lib.stream_ptr()), "fr_sum_rows")
+            tops = [total] + [None] * (len(r) - 1)
         return (None, None, *tops, *bottoms)
 
 

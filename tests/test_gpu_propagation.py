@@ -32,7 +32,7 @@ def to_torch_sparse(rp, col, val, n_rows, n_cols):
 
 
 @pytest.mark.parametrize("d", [32, 64, 128])
-@pytest.mark.parametrize("case", ["ragged", "long", "huge", "empty", "single"])
+@pytest.mark.parametrize("case", ["ragged", "long", "huge", "many_rows", "empty", "single"])
 def test_spmm_matches_sparse_mm(d, case):
     from foodrec_b200 import graph as G, ops
     rng = np.random.default_rng(1)
@@ -43,6 +43,8 @@ def test_spmm_matches_sparse_mm(d, case):
         degs = np.array([5000, 128, 129, 256, 0, 1, 2999, 127, 640] + list(rng.integers(0, 300, size=300)))
     elif case == "huge":  # thousands of segments per row: the two-level fold (children of ~sqrt(k) segments + a parent)
         degs = np.array([300000, 3, 70000, 64 * 16, 64 * 16 + 1, 64 * 17] + list(rng.integers(0, 90, size=200)))
+    elif case == "many_rows":  # hundreds of thousands of short rows (grid of > 8 000 blocks) plus a few long ones
+        degs = np.concatenate([rng.integers(0, 5, size=280000), [700, 64, 65]])
     elif case == "empty":
         degs = np.zeros(257, dtype=np.int64)
     else:

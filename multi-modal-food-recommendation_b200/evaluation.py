@@ -176,7 +176,8 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
     ~0.7 % of the kernel time (measured on the 1 M x 500 k shape: kc = 32 / 40 / 48 / 64 -> 14.2 / 15.0 / 15.8 / 17.7 ms
     per 125 000 rows) while the rows a narrow `kc` leaves uncertified cost a fixed 3.5 - 5 ms of fallback passes
     (`scripts/microbench_c4_slack.py`); with kc = k + 20 no row of that shape needs a fallback.  Default: 20 when the
-    launch is short enough for the fixed cost to matter (< ~45 ms of tensor-core time), else 12."""
+    table is wide (N >= 131 072) and the launch short enough for the fixed cost to matter (< ~45 ms of tensor-core
+    time), else 12."""
     if k < 1 or k > MAX_K:
         raise _lib.FoodRecError(f"k={k} outside [1, {MAX_K}]")
     if index_dtype not in (torch.int64, torch.int32):
@@ -192,7 +193,9 @@ def gemm_topk(A: torch.Tensor, B: torch.Tensor, k: int, *, scale: float = 1.0, b
     Bb = B_bf16 if B_bf16 is not None else to_bf16(B)
     kk = min(k, N)
     if slack is None:
-        slack = 20 if 2.0 * M * N * K < 45e-3 * 5.5e14 else 12       # ~550 TFLOP/s at K = 64
+        # (the fallback's fixed cost is a sweep over all N columns: it only outweighs the wider lists when N is large;
+        #  on the 45 000-item C2 table kc = 32 / 40 / 64 give 4.17 / 4.37 / 4.17 ms, `scripts/microbench_eval_slack.py`)
+        slack = 20 if (N >= 131072 and 2.0 * M * N * K < 45e-3 * 5.5e14) else 12       # ~550 TFLOP/s at K = 64
     kc = min(MAX_K, kk + max(int(slack), 0), N) if exact else kk
     if hist is not None:
         if row_ids is None:

@@ -43,24 +43,6 @@ inline int check_launch(const char *what) {
 __device__ __forceinline__ float4 ldg_f4(const float *p) {
     return __ldg(reinterpret_cast<const float4 *>(p));
 }
-// Streamed read-only operands (col / val / Z: touched once per launch): do not allocate in L1, so the L1 lines stay
-// with the gathered rows of X -- the only operand with reuse inside an SM (popular rows are gathered again and again).
-__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int ldg_stream_i32(const int *p) {
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ldg_stream_f32(const float *p) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
 // L2-only load: data produced by other CTAs of the SAME launch (never cached in L1).
 __device__ __forceinline__ float4 ldcg_f4(const float *p) {
     return __ldcg(reinterpret_cast<const float4 *>(p));

@@ -54,7 +54,7 @@ __device__ __forceinline__ bool epilogue_store(float4 acc, int row, int off, con
     float4 y = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
     const size_t o = (size_t)row * D + off;
     if (Z != nullptr) {
-        const float4 z = fr::ldg_stream_f4(Z + o);
+        const float4 z = fr::ldg_f4(Z + o);
         y.x = fmaf(beta, z.x, y.x);
         y.y = fmaf(beta, z.y, y.y);
         y.z = fmaf(beta, z.z, y.z);
@@ -117,8 +117,8 @@ spmm_group_body(const long long w, const int4 *__restrict__ seg, long long n_seg
         int c = 0;
         float v = 0.f;
         if (lg < cnt) {
-            c = fr::ldg_stream_i32(cp + base + lg);
-            v = fr::ldg_stream_f32(vp + base + lg);
+            c = __ldg(cp + base + lg);
+            v = __ldg(vp + base + lg);
             if (MASKED && sp.x_mask[c] == 0) c = -1;      // source row is all zeros: nothing to gather
         }
         const int lim = min(LPR, maxlen - base);

@@ -53,8 +53,10 @@ int fr_profile_dump(char *buf, int64_t cap);
  *
  *   fr_spmm_plan_sizes : from `row_ptr_host` compute n_seg, n_long (fold entries of the rows split in >1 segment),
  *                        n_part (partial-row slots of the fold workspace).
- *   fr_spmm_plan_fill  : fill host arrays seg[n_seg*4] (row, start, len, long_id|-1),
- *                        long_rows[n_long*4] (first_seg, n_parts, part_base, row).  A row of more than 16 segments folds
+ *   fr_spmm_plan_fill  : fill host arrays seg[n_seg*4] ((row, start, len, -1) for a whole row, (slot, start, len, entry)
+ *                        for a segment of a long row), long_rows[n_long*4] (first segment within the row, n_parts,
+ *                        part_base, row).  Graphs of >= 262 144 rows schedule their long-row segments by relative position
+ *                        inside the row (L2 reuse across popular rows; results unchanged).  A row of more than 16 segments folds
  *                        in two levels: ~sqrt(k) child entries (first_seg, n_parts, part_base, -(parent + 1)), contiguous
  *                        and directly followed by their parent entry (first_child, n_children, part_base, row), so the
  *                        serial chain of the last arriver is ~2 sqrt(k) loads instead of k.  The shape depends on the

@@ -136,12 +136,17 @@ def interactions_from_pickle(pickle_path: str, cache_path: str | None = None):
 
 
 # --------------------------------------------------------------------------------------------- graphs
+# Layout version of the stored segment plan (`fr_spmm_plan_fill`): 3 = long-row segments carry their fold slot, two-level
+# fold entries.  A file written with another layout is rejected (the caller rebuilds the graph and saves it again).
+PLAN_VERSION = 3
+
+
 def save_graph(path: str, g) -> None:
     """A built `graph.PropGraph`: CSR payload, segment plan and whether it is its own transpose."""
     if g.T is not None and g.T is not g:
         raise ValueError("save_graph stores symmetric graphs (g.T is g) or graphs without a transpose; save g.T separately")
     save_arrays(path, meta={"n_rows": g.n_rows, "n_cols": g.n_cols, "nnz": g.nnz, "n_seg": g.n_seg, "n_long": g.n_long,
-                            "n_part": g.n_part, "symmetric": g.T is g},
+                            "n_part": g.n_part, "symmetric": g.T is g, "plan_version": PLAN_VERSION},
                 row_ptr=g.row_ptr_host, col=g.col.cpu().numpy(), val=g.val.cpu().numpy(), seg=g.seg_host,
                 long_rows=g.long_rows_host)
 
@@ -150,5 +155,7 @@ def load_graph(path: str, device):
     """-> `graph.PropGraph` with the stored plan adopted as is (no degree pass, no plan build)."""
     from .graph import PropGraph
     a, meta = load_arrays(path)
+    if meta.get("plan_version") != PLAN_VERSION:
+        raise ValueError(f"{path}: segment plan layout {meta.get('plan_version')} != {PLAN_VERSION}; rebuild the graph and save it again")
     return PropGraph.from_plan(a["row_ptr"], a["col"], a["val"], meta["n_cols"], device, a["seg"], a["long_rows"],
                                (meta["n_seg"], meta["n_long"], meta["n_part"]), symmetric=bool(meta["symmetric"]))

@@ -89,18 +89,19 @@ def _interpret_plan(g, rp, col, val, X):
         else:
             parent = -row - 1
             publish(parent, entry - lr[parent][0], tot)
-    for i, (r, st, ln, lid) in enumerate(seg):
+    for r, st, ln, lid in seg:
         acc = (val[st:st + ln, None] * X[col[st:st + ln]]).sum(0) if ln else np.zeros(X.shape[1])
         if lid < 0:
             Y[r] = acc
             written[r] += 1
         else:
-            publish(lid, i - lr[lid][0], acc)
+            publish(lid, r, acc)             # a long-row segment carries its slot in the first field
     assert (written == 1).all() and (arrived == lr[:, 1]).all() if g.n_long else (written == 1).all()
     return Y
 
 
-@pytest.mark.parametrize("degs", [[0, 1, 128, 129, 0, 1000, 5, 256, 0], [], [0, 0], [4000], [64 * 16, 64 * 16 + 1, 70000, 3, 64 * 290]])
+@pytest.mark.parametrize("degs", [[0, 1, 128, 129, 0, 1000, 5, 256, 0], [], [0, 0], [4000], [64 * 16, 64 * 16 + 1, 70000, 3, 64 * 290],
+                                  [3000, 200] + [1] * 262144 + [2000, 65]])   # >= 262 144 rows: long segments ordered by position
 def test_segment_plan_covers_every_nonzero_once(degs):
     rp = np.concatenate([[0], np.cumsum(degs)]).astype(np.int32)
     rng = np.random.default_rng(len(degs))
@@ -112,29 +113,48 @@ def test_segment_plan_covers_every_nonzero_once(degs):
     assert g.n_seg == sum(max(1, -(-d // G.SEG)) for d in degs)
     seen = np.zeros(int(rp[-1]), dtype=np.int32)
     rows_seen = set()
+    lr = g.long_rows_host[:g.n_long]
+
+    def row_of(entry):                       # a child entry names its parent, the parent (or a single-level entry) the row
+        return int(lr[entry][3]) if lr[entry][3] >= 0 else row_of(-int(lr[entry][3]) - 1)
     for r, s, l, lid in seg:
+        if lid >= 0:                         # (slot, start, len, entry): the row comes from the fold entry
+            assert 0 <= r < lr[lid][1]
+            r = row_of(lid)
         assert 0 <= l <= G.SEG and rp[r] <= s and s + l <= rp[r + 1]
         seen[s:s + l] += 1
         rows_seen.add(int(r))
         assert (lid >= 0) == (degs[r] > G.SEG)
     assert (seen == 1).all() and rows_seen == set(range(len(degs)))
-    lr = g.long_rows_host[:g.n_long]
     ks = [-(-d // G.SEG) for d in degs if d > G.SEG]
     assert g.n_long == sum(1 + (_fold_shape(k)[1] if _fold_shape(k)[1] else 0) for k in ks)
     assert g.n_part == sum(k + _fold_shape(k)[1] for k in ks)
     slots = np.zeros(max(g.n_part, 1), np.int32)
     for k, (first, nparts, pbase, row) in enumerate(lr):
         slots[pbase:pbase + nparts] += 1
-        if row >= 0 and not (k > 0 and lr[k - 1][3] == -(k + 1)):          # a single-level row
-            assert (seg[first:first + nparts, 0] == row).all() and (seg[first:first + nparts, 3] == k).all()
-            assert nparts <= 16
+        mine = seg[seg[:, 3] == k]
+        if row >= 0 and not (k > 0 and lr[k - 1][3] == -(k + 1)):          # a single-level row: every slot once
+            assert sorted(mine[:, 0].tolist()) == list(range(nparts)) and nparts <= 16
         elif row >= 0:                                                   # a parent: its children precede it, contiguously
-            assert first + nparts == k and (lr[first:k, 3] == -(k + 1)).all()
+            assert first + nparts == k and (lr[first:k, 3] == -(k + 1)).all() and len(mine) == 0
         else:                                                            # a child
             parent = -row - 1
             assert lr[parent][3] >= 0 and lr[parent][0] <= k < parent
-            assert (seg[first:first + nparts, 0] == lr[parent][3]).all() and (seg[first:first + nparts, 3] == k).all()
+            assert sorted(mine[:, 0].tolist()) == list(range(nparts))
+            # slot j of the entry is segment first + j of the row
+            r0 = lr[parent][3]
+            assert all(int(st) == rp[r0] + (first + int(sl)) * G.SEG for sl, st in mine[:, :2])
     assert (slots[:g.n_part] == 1).all()
+    # order of the long-row block: row after row for small graphs, by relative position inside the row from 262 144 rows up
+    long_seg = seg[seg[:, 3] >= 0]
+    if len(long_seg):
+        rows_l = np.array([row_of(e) for e in long_seg[:, 3]])
+        idx_in_row = (long_seg[:, 1] - rp[rows_l]) // G.SEG
+        k_of = -(-np.asarray(degs)[rows_l] // G.SEG)
+        if len(degs) >= 262144:
+            assert (np.diff((idx_in_row << 16) // k_of) >= 0).all() and len(set(rows_l[:4].tolist())) > 1
+        else:
+            assert (np.diff(rows_l) >= 0).all()
     # whole-row segments come sorted by descending length
     single = seg[seg[:, 3] < 0][:, 2]
     assert (np.diff(single) <= 0).all()

@@ -91,6 +91,54 @@ def grads_np(model, names):
     return g
 
 
+SCALE_ROWS = 256      # sampled rows per table in the larger-scale goldens (whole tables would be tens of MB)
+
+
+def clussl_at_scale(scale):
+    """The reference's CLUSSL (`PRICAI_ModelX`) executed on the synthetic C1 / Foodcom-scale C3 data (BASELINE.json
+    configs[0] / configs[2] sizes): one batch of 512 from the seed-999 initial state.  Stored: every loss term (fp64
+    print of the fp32 values), `SCALE_ROWS` sampled rows of each forward table and of each parameter gradient (the rows
+    the batch touches first), the batch, and sampled rows of the initial parameters (so a test can verify it starts
+    from the same state without shipping the tables)."""
+    ds = make_dataset(scale)
+    batch = sample_train_batches(ds, 512, 1, seed=3)[0]
+    cfg = Cfg({**BASE, **CFGS["PRICAI_ModelX"], "n_cluster": ds.cfg.n_cluster, "train_batch_size": 512})
+    torch.manual_seed(999)
+    m = PRICAI_ModelX(cfg, ds)
+    rng = np.random.default_rng(17)
+    g = {}
+    names = ("user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight",
+             "image_prototype_embedding.weight", "text_prototype_embedding.weight")
+    touched = {"user_embedding.weight": np.unique(batch["u_id"]),
+               "item_embedding.weight": np.unique(np.concatenate([batch["pos_i_id"], batch["neg_i_id"]]))}
+    params = dict(m.named_parameters())
+    rows = {}
+    for k in names:
+        n = params[k].shape[0]
+        t = touched.get(k, np.empty(0, np.int64))[:SCALE_ROWS // 2]
+        rows[k] = np.unique(np.concatenate([t, rng.choice(n, size=min(n, SCALE_ROWS - t.size), replace=False)]))
+        g[f"rows/{k}"] = rows[k]
+        g[f"sd_rows/{k}"] = params[k].detach().numpy()[rows[k]].copy()
+        g[f"sd_sum/{k}"] = np.array(params[k].detach().double().sum().item())
+    ua, ia, (vi, vt, vg) = m.forward()
+    g["fwd/user_all"] = ua.detach().numpy()[rows["user_embedding.weight"]].copy()
+    g["fwd/item_all"] = ia.detach().numpy()[rows["item_embedding.weight"]].copy()
+    g["fwd/item_image"] = vi.detach().numpy()[rows["item_embedding.weight"]].copy()
+    g["fwd/item_text"] = vt.detach().numpy()[rows["item_embedding.weight"]].copy()
+    g["fwd/item_ingre"] = vg.detach().numpy()[rows["item_embedding.weight"]].copy()
+    m.zero_grad()
+    losses = m.calculate_loss(to_t(batch))
+    sum(losses).backward()
+    g["loss"] = np.array([float(x) for x in losses], dtype=np.float64)
+    for k in names:
+        g[f"grad/{k}"] = params[k].grad.detach().numpy()[rows[k]].copy()
+        g[f"grad_absmax/{k}"] = np.array(float(params[k].grad.abs().max()))
+    for k in ("u_id", "pos_i_id", "neg_i_id"):
+        g[f"batch/{k}"] = batch[k]
+    np.savez_compressed(os.path.join(HERE, f"clussl_{scale.lower()}.npz"), **g)
+    return len(g)
+
+
 def main():
     torch.manual_seed(999)
     np.random.seed(999)
@@ -264,6 +312,8 @@ def main():
     g["rank/by_user"] = np.array([r, n, get_auc_fast(range(2), np.array([0.9, 0.1, 0.5, 0.3, 0.05, 0.7]), 4)])
     np.savez_compressed(os.path.join(HERE, "primitives.npz"), **g)
     out["primitives"] = len(g)
+    for scale in ("C1", "C3"):
+        out["clussl_" + scale] = clussl_at_scale(scale)
     print(out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -108,6 +108,29 @@ def test_clussl_train_step_vs_oracle(scale):
             g = p_.grad.cpu()
             e32, e64, o64 = rel(g, g32[name]), rel(g, g64[name]), rel(g32[name], g64[name])
             assert e32 <= 2e-5 or e64 <= o64 + 2e-5, (name, e32, e64, o64)
+    # ... and against the REFERENCE itself executed on this very dataset and batch (tests/golden/clussl_{c1,c3}.npz,
+    # produced by make_golden.py from /root/reference): same initial parameters, losses and tables to 1e-5, gradients
+    # by the same criterion with the reference's sampled rows in the role of the fp32 oracle
+    ref = load_golden(f"clussl_{scale.lower()}.npz")
+    for k in ("u_id", "pos_i_id", "neg_i_id"):
+        assert np.array_equal(ref["batch/" + k], batch[k])
+    for name, p_ in m.named_parameters():
+        if "rows/" + name in ref:
+            assert np.array_equal(sd[name].numpy()[ref["rows/" + name]], ref["sd_rows/" + name]), name
+    close(torch.stack([x.reshape(()) for x in got]), ref["loss"])
+    ru, ri = (torch.from_numpy(ref["rows/" + k]).cuda() for k in ("user_embedding.weight", "item_embedding.weight"))
+    ua, ia, (vi, vt, vg) = m.forward()
+    for t, rows, key in ((ua, ru, "user_all"), (ia, ri, "item_all"), (vi, ri, "item_image"), (vt, ri, "item_text"),
+                         (vg, ri, "item_ingre")):
+        close(t[rows], ref["fwd/" + key])
+    for name, p_ in m.named_parameters():
+        if "grad/" + name in ref:
+            rows = torch.from_numpy(ref["rows/" + name])
+            scale_g = float(ref["grad_absmax/" + name])
+            e_ref = float((p_.grad.cpu()[rows].double() - torch.from_numpy(ref["grad/" + name]).double()).abs().max()) / scale_g
+            e64 = float((p_.grad.cpu()[rows].double() - g64[name][rows]).abs().max()) / scale_g
+            r64 = float((torch.from_numpy(ref["grad/" + name]).double() - g64[name][rows]).abs().max()) / scale_g
+            assert e_ref <= 2e-5 or e64 <= r64 + 2e-5, (name, e_ref, e64, r64)
 
 
 def test_grouped_item_side_launch_equals_separate_streams(mini_ds, mini_batches):

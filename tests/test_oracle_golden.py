@@ -1,6 +1,7 @@
 """Pin the CPU oracle to outputs of the reference itself (tests/golden/*.npz, made by
 tests/golden/make_golden.py in the build container).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from conftest import load_golden
@@ -75,6 +76,57 @@ def test_clussl_forward_loss_grad(mini_ds):
             close(got, g[f"grad/{k}/{b}"], rtol=5e-4)
     close(ranking.inference_scores(ua, ia, torch.full((len(g["infer/cand"]),), 3), T(g["infer/cand"])).numpy(),
           g["infer/scores"])
+
+
+@pytest.mark.parametrize("scale", ["C1", "C3"])
+def test_clussl_oracle_matches_reference_run_at_scale(scale):
+    """The oracle against the REFERENCE executed at C1 and at the Foodcom-scale C3 (BASELINE.json configs[2]):
+    `tests/golden/clussl_{c1,c3}.npz` hold the reference's loss terms and sampled rows of its forward tables and
+    parameter gradients for one batch of 512 from the seed-999 initial state.  The drop-in's constructor must start from
+    bit-identical parameters; losses and tables agree to 1e-6.  Gradients fed by `correlation_distance` agree to
+    1e-5 .. 5e-5 only -- that IS the fp32 run-to-run spread of the reference's own arithmetic (same torch ops, another
+    summation order inside BLAS), the yardstick the GPU tolerances are stated against."""
+    import foodrec_b200  # noqa: F401
+    from foodrec_b200.models.pricai_modelx import PRICAI_ModelX
+    from foodrec_b200.synth import make_dataset
+    g = load_golden(f"clussl_{scale.lower()}.npz")
+    ds = make_dataset(scale)
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+    cfg = Cfg(device="cpu", embedding_size=64, train_batch_size=512, is_multimodal_model=True, end2end=False,
+              use_health_level_multi_hot=True, n_ri_layers=2, n_mm_layers=1, n_ui_layers=1, reg_weight=0.01, loss_cl=0.1,
+              n_cluster=ds.cfg.n_cluster)
+    torch.manual_seed(999)
+    sd = {k: v.clone() for k, v in PRICAI_ModelX(cfg, ds).state_dict().items()}
+    names = [k[len("sd_rows/"):] for k in g if k.startswith("sd_rows/")]
+    for k in names:                                      # same seed => the reference's own initial parameters
+        assert np.array_equal(sd[k].numpy()[g["rows/" + k]], g["sd_rows/" + k]), k
+        assert float(sd[k].double().sum()) == float(g["sd_sum/" + k]), k
+    P = {k: sd[k].clone().requires_grad_(True) for k in names}
+    S = [adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items),
+         adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients),
+         adjacency.norm_adj_item_side(ds.image_cluster_triples, ds.n_items, ds.cfg.n_cluster),
+         adjacency.norm_adj_item_side(ds.text_cluster_triples, ds.n_items, ds.cfg.n_cluster)]
+    order = ("user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight",
+             "image_prototype_embedding.weight", "text_prototype_embedding.weight")
+    out = propagation.clussl_forward(*S, *(P[k] for k in order), ds.n_users, ds.n_items, ds.num_ingredients,
+                                     ds.cfg.n_cluster, 2, 1)
+    u, p, n = (torch.from_numpy(g["batch/" + k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+    terms = losses.clussl_loss(out, P["user_embedding.weight"], P["item_embedding.weight"], u, p, n, 0.01, 0.1)
+    sum(terms).sum().backward()
+    assert np.allclose([float(t) for t in terms], g["loss"], rtol=1e-6, atol=0)
+    ru, ri = g["rows/user_embedding.weight"], g["rows/item_embedding.weight"]
+    views = out[2]
+    for got, rows, key in ((out[0], ru, "user_all"), (out[1], ri, "item_all"), (views[0], ri, "item_image"),
+                           (views[1], ri, "item_text"), (views[2], ri, "item_ingre")):
+        a, b = got.detach().numpy()[rows], g["fwd/" + key]
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), key
+    for k in order:
+        a, b = P[k].grad.numpy()[g["rows/" + k]], g["grad/" + k]
+        tol = 1e-6 if k == "user_embedding.weight" else 2e-4
+        assert np.abs(a - b).max() <= tol * float(g["grad_absmax/" + k]), k
 
 
 def test_healthrec_forward(mini_ds, mini_batches):

@@ -139,6 +139,53 @@ def clussl_at_scale(scale):
     return len(g)
 
 
+def healthrec_c1():
+    """BASELINE.json configs[0]: the reference's HealthRec (`CIKM_Model`) executed on the synthetic C1 data (5 000 users,
+    3 000 items, 50 000 interactions, d = 64, 2 + 1 layers) on the CPU: one batch of 512 from the seed-999 initial state,
+    transformer dropout off (`eval()`).  Stored like `clussl_at_scale`: loss terms, sampled rows of the forward tables,
+    of the table gradients and of the initial parameters, the two projection gradients in full, the batch."""
+    ds = make_dataset("C1")
+    batch = sample_train_batches(ds, 512, 1, seed=3)[0]
+    cfg = Cfg({**BASE, **CFGS["CIKM_Model"], "train_batch_size": 512})
+    torch.manual_seed(999)
+    m = CIKM_Model(cfg, ds)
+    m.eval()
+    rng = np.random.default_rng(19)
+    params = dict(m.named_parameters())
+    tables = ("user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight")
+    touched = {"user_embedding.weight": np.unique(batch["u_id"]),
+               "item_embedding.weight": np.unique(np.concatenate([batch["pos_i_id"], batch["neg_i_id"]]))}
+    g, rows = {}, {}
+    for k in tables:
+        n = params[k].shape[0]
+        t = touched.get(k, np.empty(0, np.int64))[:SCALE_ROWS // 2]
+        rows[k] = np.unique(np.concatenate([t, rng.choice(n, size=min(n, SCALE_ROWS - t.size), replace=False)]))
+        g[f"rows/{k}"] = rows[k]
+        g[f"sd_rows/{k}"] = params[k].detach().numpy()[rows[k]].copy()
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point:
+            g[f"sd_sum/{k}"] = np.array(v.double().sum().item())
+    ua, ia, ing = m.forward()
+    g["fwd/user_all"] = ua.detach().numpy()[rows["user_embedding.weight"]].copy()
+    g["fwd/item_all"] = ia.detach().numpy()[rows["item_embedding.weight"]].copy()
+    ing_rows = rows["ingre_embedding.weight"][rows["ingre_embedding.weight"] < ing.shape[0]]
+    g["rows/ingre_ir"] = ing_rows
+    g["fwd/ingre_ir"] = ing.detach().numpy()[ing_rows].copy()
+    m.zero_grad()
+    losses = m.calculate_loss(to_t(batch))
+    sum(losses).backward()
+    g["loss"] = np.array([float(x) for x in losses], dtype=np.float64)
+    for k in tables:
+        g[f"grad/{k}"] = params[k].grad.detach().numpy()[rows[k]].copy()
+        g[f"grad_absmax/{k}"] = np.array(float(params[k].grad.abs().max()))
+    for k in ("image_trs.weight", "text_trs.weight"):
+        g[f"grad_full/{k}"] = params[k].grad.detach().numpy().copy()
+    for k, v in batch.items():
+        g[f"batch/{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "healthrec_c1.npz"), **g)
+    return len(g)
+
+
 def main():
     torch.manual_seed(999)
     np.random.seed(999)
@@ -314,6 +361,7 @@ def main():
     out["primitives"] = len(g)
     for scale in ("C1", "C3"):
         out["clussl_" + scale] = clussl_at_scale(scale)
+    out["healthrec_C1"] = healthrec_c1()
     print(out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

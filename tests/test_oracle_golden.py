@@ -149,6 +149,40 @@ def test_healthrec_forward(mini_ds, mini_batches):
         close([float(mf), float(reg)], g[f"loss/{b}"][[0, 3]])
 
 
+def test_healthrec_oracle_matches_reference_run_at_c1():
+    """BASELINE.json configs[0] (HealthRec on C1, CPU): the oracle's propagation, BPR and regulariser against the
+    reference's own run (`tests/golden/healthrec_c1.npz`), from the same-seed initial parameters of the drop-in's
+    constructor (checked bit for bit against the reference's)."""
+    import foodrec_b200  # noqa: F401
+    from foodrec_b200.models.cikm_model import CIKM_Model
+    from foodrec_b200.synth import make_dataset
+    g = load_golden("healthrec_c1.npz")
+    ds = make_dataset("C1")
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+    torch.manual_seed(999)
+    m = CIKM_Model(Cfg(device="cpu", embedding_size=64, train_batch_size=512, is_multimodal_model=True, end2end=False,
+                       use_health_level_multi_hot=True, num_attention_heads=2, num_hidden_layers=2,
+                       attention_probs_dropout_prob=0.0, hidden_act="gelu", n_layers=2, ui_layers=1, reg_weight=0.5,
+                       loss_kd=0.05, loss_health=0.1, kd_threshold=0.4), ds)
+    sd = m.state_dict()
+    for k in [x[len("sd_sum/"):] for x in g if x.startswith("sd_sum/")]:
+        assert float(sd[k].double().sum()) == float(g["sd_sum/" + k]), k
+    uw, iw, gw = (sd[k] for k in ("user_embedding.weight", "item_embedding.weight", "ingre_embedding.weight"))
+    S_ui = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    S_ri = adjacency.norm_adj_item_side(ds.rIngre_triples, ds.n_items, ds.num_ingredients)
+    ua, ia, ing = propagation.healthrec_forward(S_ui, S_ri, uw, iw, gw, ds.n_users, ds.n_items, ds.num_ingredients, 2, 1)
+    close(ua.numpy()[g["rows/user_embedding.weight"]], g["fwd/user_all"])
+    close(ia.numpy()[g["rows/item_embedding.weight"]], g["fwd/item_all"])
+    close(ing.numpy()[g["rows/ingre_ir"]], g["fwd/ingre_ir"])
+    u, p, n = (T(g["batch/" + k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+    mf = losses.bpr_from_tables(ua, ia, u, p, n)
+    reg = 0.5 * losses.emb_loss(uw[u], iw[p], iw[n], gw[T(g["batch/pos_ingre_code"])], gw[T(g["batch/neg_ingre_code"])])
+    close([float(mf), float(reg)], g["loss"][[0, 3]])
+
+
 def test_lightgcn_forward(mini_ds, mini_batches):
     g = load_golden("lightgcn_mini.npz")
     ds = mini_ds

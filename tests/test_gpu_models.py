@@ -88,7 +88,7 @@ def test_healthrec_c1_matches_reference_run():
         if "grad_full/" + name in g:
             # the projections' gradients arrive through the dense torch branch (transformer / target attention on the
             # GPU here, on the CPU in the reference run): measured 2.1e-4 of the largest entry for image_trs at C1
-            check("grad_full/" + name, p.grad, g["grad_full/" + name], 5e-4, 1e-9)
+            check("grad_full/" + name, p.grad, g["grad_full/" + name], 1e-3, 1e-9)
     bad = "; ".join(f"{w} {e:.2e}" for w, e, ok in report if not ok)
     assert not bad, bad
 

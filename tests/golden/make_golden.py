@@ -186,6 +186,51 @@ def healthrec_c1():
     return len(g)
 
 
+def schgn_c1():
+    """The reference's SCHGN class executed on the synthetic C1 data (GCNConv from oracle/schgn.py, dropout = identity):
+    one batch of 256 from the seed-999 initial state -- loss terms, every small parameter's gradient in full, sampled
+    rows of the table gradients and of the GCN output, full-sort scores of three users."""
+    ds = make_dataset("C1")
+    cfg = Cfg({**BASE, **CFGS["SCHGN"], "train_batch_size": 256})
+    torch.manual_seed(999)
+    m = SCHGN(cfg, ds)
+    m.eval()
+    real_dropout = torch.nn.functional.dropout
+    torch.nn.functional.dropout = lambda x, p=0.5, training=True, inplace=False: x
+    rng = np.random.default_rng(23)
+    g = {}
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point:
+            g[f"sd_sum/{k}"] = np.array(v.double().sum().item())
+    x = torch.cat([m.user_embed, m.item_embed, m.ingre_embed_first, m.health_embed], 0)
+    gcn = m.new_gcn(x, torch.cat([m.g2i_edges, m.i2u_edges], 0).t().contiguous()).detach().numpy()
+    g["rows/gcn"] = np.sort(rng.choice(gcn.shape[0], size=SCALE_ROWS, replace=False))
+    g["gcn/out"] = gcn[g["rows/gcn"]].copy()
+    batch = sample_train_batches(ds, 256, 1, seed=3, schgn=True)[0]
+    m.zero_grad()
+    losses = m.calculate_loss(to_t(batch))
+    sum(losses).backward()
+    g["loss"] = np.array([float(x) for x in losses], dtype=np.float64)
+    for n_, p_ in m.named_parameters():
+        if p_.grad is None:
+            continue
+        gr = p_.grad.detach().numpy()
+        if gr.size <= 64 * 256:
+            g[f"grad_full/{n_}"] = gr.copy()
+        else:
+            rows = np.sort(rng.choice(gr.shape[0], size=min(SCALE_ROWS, gr.shape[0]), replace=False))
+            g[f"rows/{n_}"], g[f"grad/{n_}"] = rows, gr[rows].copy()
+            g[f"grad_absmax/{n_}"] = np.array(float(np.abs(gr).max()))
+    for k in ("masked_ingre_seq", "neg_ingre_seq", "u_id"):
+        g[f"batch/{k}"] = np.asarray(batch[k])
+    with torch.no_grad():
+        for u in (0, 7, 4999):
+            g[f"full_sort/{u}"] = m.full_sort_predict({"u_id": torch.tensor([u])}).numpy()
+    torch.nn.functional.dropout = real_dropout
+    np.savez_compressed(os.path.join(HERE, "schgn_c1.npz"), **g)
+    return len(g)
+
+
 def main():
     torch.manual_seed(999)
     np.random.seed(999)
@@ -362,6 +407,7 @@ def main():
     for scale in ("C1", "C3"):
         out["clussl_" + scale] = clussl_at_scale(scale)
     out["healthrec_C1"] = healthrec_c1()
+    out["schgn_C1"] = schgn_c1()
     print(out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

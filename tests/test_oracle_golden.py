@@ -284,3 +284,52 @@ def test_schgn_oracle_matches_reference_run(mini_ds):
     for u in (0, 7, 200):
         s = O.full_sort_scores(P, mini_ds, u, ei, sizes)
         np.testing.assert_allclose(s.numpy(), g[f"full_sort/{u}"], rtol=0, atol=1e-7)
+
+
+def test_schgn_oracle_matches_reference_run_at_c1():
+    """oracle/schgn.py vs tests/golden/schgn_c1.npz (the reference's SCHGN class executed on C1 with the GCNConv
+    stand-in; dropout = identity), from the drop-in constructor's same-seed state (every floating tensor's sum checked
+    against the reference's): GCN output rows, the three loss terms, every small parameter's gradient, sampled rows of
+    the table gradients, full-sort scores of three users."""
+    import foodrec_b200  # noqa: F401
+    from foodrec_b200.models.schgn import SCHGN
+    from foodrec_b200.synth import make_dataset, sample_train_batches
+    from oracle import schgn as O
+    g = load_golden("schgn_c1.npz")
+    ds = make_dataset("C1")
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+    torch.manual_seed(999)
+    m = SCHGN(Cfg(device="cpu", embedding_size=64, train_batch_size=256, is_multimodal_model=True, end2end=False,
+                  use_health_level_multi_hot=True, num_attention_heads=2, num_hidden_layers=2, hidden_act="gelu",
+                  inner_size=256, hidden_dropout_prob=0.5, attention_probs_dropout_prob=0.5, regs=0.01, reg_image=1,
+                  reg_w=0.05, reg_g=0.01, reg_health=0.01, ssl=0.008, SCHGN_ssl=True, neg_sample_num=4), ds)
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for k in [x[len("sd_sum/"):] for x in g if x.startswith("sd_sum/")]:
+        assert float(P[k].double().sum()) == float(g["sd_sum/" + k]), k
+    ei = O.schgn_edge_index(ds)
+    sizes = (ds.n_users, ds.n_items, ds.num_ingredients, ds.num_calories_level)
+    gcn = torch.cat(O.gcn_tables(P, ei, sizes), 0).numpy()
+    assert np.abs(gcn[g["rows/gcn"]] - g["gcn/out"]).max() <= 1e-6 * np.abs(g["gcn/out"]).max()
+    cfg = dict(regs=0.01, reg_image=1, reg_w=0.05, reg_g=0.01, reg_health=0.01, ssl=0.008, num_hidden_layers=2,
+               num_attention_heads=2)
+    batch = sample_train_batches(ds, 256, 1, seed=3, schgn=True)[0]
+    for k in ("masked_ingre_seq", "neg_ingre_seq", "u_id"):
+        assert np.array_equal(np.asarray(batch[k]), g["batch/" + k])
+    Pg = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in P.items()}
+    losses_ = O.calculate_loss(Pg, {k: torch.from_numpy(np.asarray(v)) for k, v in batch.items()}, cfg, ei, sizes)
+    np.testing.assert_allclose([float(x.detach()) for x in losses_], g["loss"], rtol=1e-6)
+    sum(losses_).backward()
+    for k, ref in g.items():
+        if k.startswith("grad_full/") and "key.bias" not in k:       # d/d(key bias) == 0 exactly
+            got = Pg[k[len("grad_full/"):]].grad.numpy()
+            assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-12, k
+        if k.startswith("grad/"):
+            name = k[len("grad/"):]
+            got = Pg[name].grad.numpy()[g["rows/" + name]]
+            assert np.abs(got - ref).max() <= 2e-5 * float(g["grad_absmax/" + name]) + 1e-12, k
+    for u in (0, 7, 4999):
+        s = O.full_sort_scores(P, ds, u, ei, sizes)
+        np.testing.assert_allclose(s.numpy(), g[f"full_sort/{u}"], rtol=0, atol=2e-6)

@@ -231,6 +231,38 @@ def schgn_c1():
     return len(g)
 
 
+def lightgcn_c1():
+    """The reference's LightGCN executed on the synthetic C1 data: one batch of 512 from the seed-999 initial state."""
+    ds = make_dataset("C1")
+    batch = sample_train_batches(ds, 512, 1, seed=3)[0]
+    cfg = Cfg({**BASE, **CFGS["LightGCN"], "train_batch_size": 512})
+    torch.manual_seed(999)
+    m = LightGCN(cfg, ds)
+    rng = np.random.default_rng(29)
+    g = {}
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point:
+            g[f"sd_sum/{k}"] = np.array(v.double().sum().item())
+    ru = np.unique(np.concatenate([np.unique(batch["u_id"])[:SCALE_ROWS // 2], rng.choice(ds.n_users, SCALE_ROWS // 2, replace=False)]))
+    ri = np.unique(np.concatenate([np.unique(batch["pos_i_id"])[:SCALE_ROWS // 2], rng.choice(ds.n_items, SCALE_ROWS // 2, replace=False)]))
+    g["rows/user"], g["rows/item"] = ru, ri
+    ua, ia = m.forward()
+    g["fwd/user_all"], g["fwd/item_all"] = ua.detach().numpy()[ru].copy(), ia.detach().numpy()[ri].copy()
+    m.zero_grad()
+    losses = m.calculate_loss(to_t(batch))
+    sum(losses).backward()
+    g["loss"] = np.array([float(x) for x in losses], dtype=np.float64)
+    params = dict(m.named_parameters())
+    g["grad/user_embedding.weight"] = params["user_embedding.weight"].grad.detach().numpy()[ru].copy()
+    g["grad_absmax/user_embedding.weight"] = np.array(float(params["user_embedding.weight"].grad.abs().max()))
+    for k in ("image_trs.weight", "image_trs.bias"):
+        g[f"grad_full/{k}"] = params[k].grad.detach().numpy().copy()
+    for k in ("u_id", "pos_i_id", "neg_i_id"):
+        g[f"batch/{k}"] = batch[k]
+    np.savez_compressed(os.path.join(HERE, "lightgcn_c1.npz"), **g)
+    return len(g)
+
+
 def main():
     torch.manual_seed(999)
     np.random.seed(999)
@@ -408,6 +440,7 @@ def main():
         out["clussl_" + scale] = clussl_at_scale(scale)
     out["healthrec_C1"] = healthrec_c1()
     out["schgn_C1"] = schgn_c1()
+    out["lightgcn_C1"] = lightgcn_c1()
     print(out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -333,3 +333,29 @@ def test_schgn_oracle_matches_reference_run_at_c1():
     for u in (0, 7, 4999):
         s = O.full_sort_scores(P, ds, u, ei, sizes)
         np.testing.assert_allclose(s.numpy(), g[f"full_sort/{u}"], rtol=0, atol=2e-6)
+
+
+def test_lightgcn_oracle_matches_reference_run_at_c1():
+    """The oracle's LightGCN forward and BPR term against the reference executed on C1 (`lightgcn_c1.npz`), from the
+    drop-in constructor's same-seed state (sums checked against the reference's)."""
+    import foodrec_b200  # noqa: F401
+    from foodrec_b200.models.lightgcn import LightGCN
+    from foodrec_b200.synth import make_dataset
+    g = load_golden("lightgcn_c1.npz")
+    ds = make_dataset("C1")
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+    torch.manual_seed(999)
+    sd = LightGCN(Cfg(device="cpu", embedding_size=64, train_batch_size=512, is_multimodal_model=True, end2end=False,
+                      use_health_level_multi_hot=True, n_layers=2, reg_weight=0.1), ds).state_dict()
+    for k in [x[len("sd_sum/"):] for x in g if x.startswith("sd_sum/")]:
+        assert float(sd[k].double().sum()) == float(g["sd_sum/" + k]), k
+    S_ui = adjacency.norm_adj_user_item(ds.train_coo_matrix, ds.n_users, ds.n_items)
+    ego = sd["image_embedding.weight"] @ sd["image_trs.weight"].t() + sd["image_trs.bias"]
+    ua, ia = propagation.lightgcn_forward(S_ui, sd["user_embedding.weight"], ego, ds.n_users, ds.n_items, 2)
+    close(ua.numpy()[g["rows/user"]], g["fwd/user_all"])
+    close(ia.numpy()[g["rows/item"]], g["fwd/item_all"])
+    u, p, n = (T(g["batch/" + k]) for k in ("u_id", "pos_i_id", "neg_i_id"))
+    close(float(losses.bpr_from_tables(ua, ia, u, p, n)), g["loss"][0])
